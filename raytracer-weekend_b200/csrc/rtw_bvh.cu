@@ -1,0 +1,552 @@
+// LBVH build on the GPU: per-primitive world boxes -> scene bounds ->
+// 63-bit Morton codes -> LSD radix sort -> Karras 2012 hierarchy -> atomic bottom-up refit.
+//
+// Node layout in HBM: internal node i owns the 64-byte PAIR nodes[2i], nodes[2i+1] = the records
+// of its left and right child (32 bytes each: box + link + meta, see rtw_bvh_node).  One traversal
+// step fetches a pair with four LDG.128 and knows both child boxes, so it can descend front to back.
+//
+// Boxes follow the reference's bounding_box() of every primitive (cited per case) pushed through
+// the instance chain the way Translation / YRotation do it (transformations.rs:40-47, 77-111), and
+// are then padded by 2^-20 of the scene's largest coordinate: the traversal tests primitives in
+// OBJECT space with a transformed ray whose rounding differs from the world-space slab test.
+#include <algorithm>
+#include <cfloat>
+#include <cstdio>
+#include <cstring>
+
+#include "rtw_scene.cuh"
+
+namespace rtw {
+
+namespace {
+
+// ---- helpers -----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t f2ord(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ord2f(uint32_t u) {
+  uint32_t b = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+  float f;
+#ifdef __CUDA_ARCH__
+  f = __uint_as_float(b);
+#else
+  memcpy(&f, &b, 4);
+#endif
+  return f;
+}
+
+struct Box {
+  v3 lo, hi;
+};
+
+// triangular.rs:79-93
+__device__ __forceinline__ void tri_min_max(float a, float b, float c, float& lo, float& hi) {
+  lo = fminf(a, fminf(b, c));
+  hi = fmaxf(a, fmaxf(b, c));
+  if (fabsf(lo - hi) < 0.0002f) { lo = lo - 0.0001f; hi = hi + 0.0001f; }
+}
+
+// transformations.rs:77-111
+__device__ __forceinline__ Box rotate_box(Box b, float sin_theta, float cos_theta) {
+  const float INF = __int_as_float(0x7f800000);
+  v3 mn = mk(INF, INF, INF), mx = mk(-INF, -INF, -INF);
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 2; ++j)
+      for (int k = 0; k < 2; ++k) {
+        float fi = (float)i, fj = (float)j, fk = (float)k;
+        float x = fi * b.hi.x + (1.0f - fi) * b.lo.x;
+        float y = fj * b.hi.y + (1.0f - fj) * b.lo.y;
+        float z = fk * b.hi.z + (1.0f - fk) * b.lo.z;
+        float new_x = cos_theta * x + sin_theta * z;
+        float new_z = (-sin_theta) * x + cos_theta * z;
+        mn.x = fminf(mn.x, new_x); mx.x = fmaxf(mx.x, new_x);
+        mn.y = fminf(mn.y, y);     mx.y = fmaxf(mx.y, y);
+        mn.z = fminf(mn.z, new_z); mx.z = fmaxf(mx.z, new_z);
+      }
+  Box r; r.lo = mn; r.hi = mx;
+  return r;
+}
+
+// Kernel 1: object-space box per the reference, pushed through the instance chain; also rewrites
+// the raw parameters into the traversal encoding (canonical order).
+//   raw SPHERE  g0=(c, r)
+//   raw MSPHERE g0=(c0, r) g1=(c1, time0) g2=(time1)      -> enc g1=(c1-c0, time0) g2=(time1-time0)
+//   raw RECT    g0=(a0,a1,b0,b1) g1=(k)
+//   raw TRI     g0=(a, b.x) g1=(b.yz, c.xy) g2=(c.z)       -> enc (a, e1, e2, n) in 12 floats
+__global__ void k_prim_setup(uint32_t n, const float4* __restrict__ raw, const uint32_t* __restrict__ meta,
+                             const uint2* __restrict__ inst_range, const InstOp* __restrict__ inst_ops, float time0,
+                             float time1, float4* __restrict__ enc, float4* __restrict__ box_lo,
+                             float4* __restrict__ box_hi) {
+  uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= n) return;
+  float4 g0 = raw[3 * (size_t)id], g1 = raw[3 * (size_t)id + 1], g2 = raw[3 * (size_t)id + 2];
+  uint32_t m = meta[id];
+  uint32_t type = m & 7u, inst = m >> RTW_META_TYPE_BITS;
+  Box b;
+  switch (type) {
+    case PT_SPHERE: {  // spherical.rs:98-104 ; [QUIRK] negative radius gives min > max there: use |r|
+      float r = fabsf(g0.w);
+      v3 c = mk(g0.x, g0.y, g0.z), rv = mk(r, r, r);
+      b.lo = c - rv; b.hi = c + rv;
+      break;
+    }
+    case PT_MSPHERE: {  // spherical.rs:138-150
+      v3 c0 = mk(g0.x, g0.y, g0.z), c1 = mk(g1.x, g1.y, g1.z);
+      float t0 = g1.w, t1 = g2.x;
+      v3 dc = c1 - c0;
+      float dt = t1 - t0;
+      g1 = make_float4(dc.x, dc.y, dc.z, t0);
+      g2 = make_float4(dt, 0.f, 0.f, 0.f);
+      v3 sc = c0 + ((time0 - t0) / dt) * dc;
+      v3 ec = c0 + ((time1 - t0) / dt) * dc;
+      float r = fabsf(g0.w);
+      v3 rv = mk(r, r, r);
+      b.lo = mk(fminf(sc.x - rv.x, ec.x - rv.x), fminf(sc.y - rv.y, ec.y - rv.y), fminf(sc.z - rv.z, ec.z - rv.z));
+      b.hi = mk(fmaxf(sc.x + rv.x, ec.x + rv.x), fmaxf(sc.y + rv.y, ec.y + rv.y), fmaxf(sc.z + rv.z, ec.z + rv.z));
+      break;
+    }
+    case PT_RECT_YZ:  // rectangular.rs:161-166
+      b.lo = mk(g1.x - 0.0001f, g0.x, g0.z); b.hi = mk(g1.x + 0.0001f, g0.y, g0.w);
+      break;
+    case PT_RECT_XZ:  // rectangular.rs:110-115
+      b.lo = mk(g0.x, g1.x - 0.0001f, g0.z); b.hi = mk(g0.y, g1.x + 0.0001f, g0.w);
+      break;
+    case PT_RECT_XY:  // rectangular.rs:59-64
+      b.lo = mk(g0.x, g0.z, g1.x - 0.0001f); b.hi = mk(g0.y, g0.w, g1.x + 0.0001f);
+      break;
+    default: {  // triangular.rs:140-149 ; encode triangular.rs:101-103
+      v3 va = mk(g0.x, g0.y, g0.z), vb = mk(g0.w, g1.x, g1.y), vc = mk(g1.z, g1.w, g2.x);
+      tri_min_max(va.x, vb.x, vc.x, b.lo.x, b.hi.x);
+      tri_min_max(va.y, vb.y, vc.y, b.lo.y, b.hi.y);
+      tri_min_max(va.z, vb.z, vc.z, b.lo.z, b.hi.z);
+      v3 e1 = vb - va, e2 = vc - va;
+      v3 nn = cross(e1, e2);
+      g0 = make_float4(va.x, va.y, va.z, e1.x);
+      g1 = make_float4(e1.y, e1.z, e2.x, e2.y);
+      g2 = make_float4(e2.z, nn.x, nn.y, nn.z);
+      break;
+    }
+  }
+  enc[3 * (size_t)id] = g0; enc[3 * (size_t)id + 1] = g1; enc[3 * (size_t)id + 2] = g2;
+  if (inst != 0) {
+    uint2 rg = inst_range[inst];
+    for (int k = (int)rg.y - 1; k >= 0; --k) {  // innermost wrapper first
+      InstOp op = inst_ops[rg.x + k];
+      if (op.kind == OP_TRANSLATE) {  // transformations.rs:40-47
+        v3 off = mk(op.a, op.b, op.c);
+        b.lo = b.lo + off; b.hi = b.hi + off;
+      } else {
+        b = rotate_box(b, op.a, op.b);
+      }
+    }
+  }
+  box_lo[id] = make_float4(b.lo.x, b.lo.y, b.lo.z, 0.f);
+  box_hi[id] = make_float4(b.hi.x, b.hi.y, b.hi.z, 0.f);
+}
+
+// Kernel 2: bounds of the box centroids (6 ordered uints) and the largest finite |coordinate| (1).
+__global__ void k_bounds(uint32_t n, const float4* __restrict__ box_lo, const float4* __restrict__ box_hi,
+                         uint32_t* __restrict__ out /*7*/) {
+  const float INF = __int_as_float(0x7f800000);
+  float mn[3] = {INF, INF, INF}, mx[3] = {-INF, -INF, -INF};
+  float amax = 0.f;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float4 lo = box_lo[i], hi = box_hi[i];
+    float c[3] = {0.5f * lo.x + 0.5f * hi.x, 0.5f * lo.y + 0.5f * hi.y, 0.5f * lo.z + 0.5f * hi.z};
+    float e[6] = {lo.x, lo.y, lo.z, hi.x, hi.y, hi.z};
+    for (int a = 0; a < 3; ++a)
+      if (isfinite(c[a])) { mn[a] = fminf(mn[a], c[a]); mx[a] = fmaxf(mx[a], c[a]); }
+    for (int a = 0; a < 6; ++a)
+      if (isfinite(e[a])) amax = fmaxf(amax, fabsf(e[a]));
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    for (int a = 0; a < 3; ++a) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], off));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], off));
+    }
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, off));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    for (int a = 0; a < 3; ++a) {
+      atomicMin(&out[a], f2ord(mn[a]));
+      atomicMax(&out[3 + a], f2ord(mx[a]));
+    }
+    atomicMax(&out[6], f2ord(amax));
+  }
+}
+
+__device__ __forceinline__ uint64_t expand21(uint32_t v) {  // spread 21 bits to every third bit
+  uint64_t x = v & 0x1FFFFFu;
+  x = (x | (x << 32)) & 0x1F00000000FFFFull;
+  x = (x | (x << 16)) & 0x1F0000FF0000FFull;
+  x = (x | (x << 8)) & 0x100F00F00F00F00Full;
+  x = (x | (x << 4)) & 0x10C30C30C30C30C3ull;
+  x = (x | (x << 2)) & 0x1249249249249249ull;
+  return x;
+}
+
+// Kernel 3: 63-bit Morton code of the box centroid inside the centroid bounds.
+__global__ void k_morton(uint32_t n, const float4* __restrict__ box_lo, const float4* __restrict__ box_hi,
+                         const uint32_t* __restrict__ bounds, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 lo = box_lo[i], hi = box_hi[i];
+  float c[3] = {0.5f * lo.x + 0.5f * hi.x, 0.5f * lo.y + 0.5f * hi.y, 0.5f * lo.z + 0.5f * hi.z};
+  uint32_t q[3];
+  for (int a = 0; a < 3; ++a) {
+    float mn = ord2f(bounds[a]), mx = ord2f(bounds[3 + a]);
+    float ext = mx - mn;
+    float f = (ext > 0.f && isfinite(c[a])) ? (c[a] - mn) / ext : 0.f;
+    f = fminf(fmaxf(f, 0.f), 1.f);
+    q[a] = min((uint32_t)(f * 2097152.0f), 2097151u);
+  }
+  keys[i] = (expand21(q[0]) << 2) | (expand21(q[1]) << 1) | expand21(q[2]);
+  vals[i] = i;
+}
+
+// ---- LSD radix sort, 8 bits per pass, stable ---------------------------------------------------
+#define SORT_THREADS 256
+
+__global__ void k_sort_hist(uint32_t n, uint32_t chunk, const uint64_t* __restrict__ keys, int shift,
+                            uint32_t* __restrict__ hist /*[256][gridDim.x]*/) {
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  uint32_t begin = blockIdx.x * chunk;
+  uint32_t end = min(n, begin + chunk);
+  for (uint32_t i = begin + threadIdx.x; i < end; i += SORT_THREADS) atomicAdd(&h[(uint32_t)(keys[i] >> shift) & 255u], 1u);
+  __syncthreads();
+  hist[threadIdx.x * gridDim.x + blockIdx.x] = h[threadIdx.x];
+}
+
+// exclusive scan of hist (bin-major) with one block
+__global__ void k_sort_scan(uint32_t total, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < total; base += blockDim.x) {
+    uint32_t i = base + threadIdx.x;
+    uint32_t v = (i < total) ? hist[i] : 0u;
+    uint32_t x = v;
+    for (int off = 1; off < 32; off <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, x, off);
+      if ((threadIdx.x & 31) >= off) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      uint32_t w = (threadIdx.x < (blockDim.x >> 5)) ? warp_sums[threadIdx.x] : 0u;
+      uint32_t ws = w;
+      for (int off = 1; off < 32; off <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, ws, off);
+        if (threadIdx.x >= off) ws += y;
+      }
+      warp_sums[threadIdx.x] = ws - w;  // exclusive
+    }
+    __syncthreads();
+    uint32_t excl = carry + warp_sums[threadIdx.x >> 5] + (x - v);
+    if (i < total) hist[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+    __syncthreads();
+  }
+}
+
+__global__ void k_sort_scatter(uint32_t n, uint32_t chunk, const uint64_t* __restrict__ keys_in,
+                               const uint32_t* __restrict__ vals_in, uint64_t* __restrict__ keys_out,
+                               uint32_t* __restrict__ vals_out, int shift, const uint32_t* __restrict__ hist) {
+  __shared__ uint32_t base[256];
+  __shared__ uint32_t warp_cnt[SORT_THREADS / 32][256];
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  base[threadIdx.x] = hist[threadIdx.x * gridDim.x + blockIdx.x];
+  for (uint32_t w = 0; w < SORT_THREADS / 32; ++w) warp_cnt[w][threadIdx.x] = 0;
+  __syncthreads();
+  uint32_t begin = blockIdx.x * chunk;
+  uint32_t end = min(n, begin + chunk);
+  for (uint32_t tile = begin; tile < end; tile += SORT_THREADS) {
+    uint32_t i = tile + threadIdx.x;
+    bool valid = i < end;
+    uint64_t key = valid ? keys_in[i] : 0ull;
+    uint32_t val = valid ? vals_in[i] : 0u;
+    uint32_t digit = valid ? ((uint32_t)(key >> shift) & 255u) : (256u + lane);
+    uint32_t peers = __match_any_sync(0xffffffffu, digit);
+    uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+    if (valid && rank == 0) warp_cnt[warp][digit] = __popc(peers);
+    __syncthreads();
+    if (valid) {
+      uint32_t pre = 0;
+      for (uint32_t w = 0; w < warp; ++w) pre += warp_cnt[w][digit];
+      uint32_t pos = base[digit] + pre + rank;
+      keys_out[pos] = key;
+      vals_out[pos] = val;
+    }
+    __syncthreads();
+    uint32_t tot = 0;
+    for (uint32_t w = 0; w < SORT_THREADS / 32; ++w) {
+      tot += warp_cnt[w][threadIdx.x];
+      warp_cnt[w][threadIdx.x] = 0;
+    }
+    base[threadIdx.x] += tot;
+    __syncthreads();
+  }
+}
+
+// ---- Karras 2012 ---------------------------------------------------------------------------------
+__device__ __forceinline__ int delta(const uint64_t* __restrict__ keys, int n, int i, int j) {
+  if (j < 0 || j >= n) return -1;
+  uint64_t a = keys[i], b = keys[j];
+  if (a == b) return 64 + __clz((uint32_t)i ^ (uint32_t)j);
+  return __clzll((long long)(a ^ b));
+}
+
+// parent encoding: (pair index << 1) | side
+__global__ void k_karras(int n, const uint64_t* __restrict__ keys, uint32_t* __restrict__ node_parent,
+                         uint32_t* __restrict__ leaf_parent) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1) return;
+  int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+  int dmin = delta(keys, n, i, i - d);
+  int lmax = 2;
+  while (delta(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
+  int l = 0;
+  for (int t = lmax / 2; t >= 1; t /= 2)
+    if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+  int j = i + l * d;
+  int dnode = delta(keys, n, i, j);
+  int s = 0;
+  int t = l;
+  do {
+    t = (t + 1) >> 1;
+    if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+  } while (t > 1);
+  int gamma = i + s * d + min(d, 0);
+  int lo = min(i, j), hi = max(i, j);
+  uint32_t me = (uint32_t)i << 1;
+  if (lo == gamma) leaf_parent[gamma] = me | 0u; else node_parent[gamma] = me | 0u;
+  if (hi == gamma + 1) leaf_parent[gamma + 1] = me | 1u; else node_parent[gamma + 1] = me | 1u;
+  if (i == 0) node_parent[0] = 0xFFFFFFFFu;
+}
+
+// Kernel: leaves.  Slot s holds primitive vals[s]; copies its geometry into slot order.
+__global__ void k_emit_leaves(uint32_t n, const uint32_t* __restrict__ vals, const float4* __restrict__ enc,
+                              float4* __restrict__ geom, int32_t* __restrict__ slot_prim) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  uint32_t id = vals[s];
+  slot_prim[s] = (int32_t)id;
+  geom[3 * (size_t)s] = enc[3 * (size_t)id];
+  geom[3 * (size_t)s + 1] = enc[3 * (size_t)id + 1];
+  geom[3 * (size_t)s + 2] = enc[3 * (size_t)id + 2];
+}
+
+__device__ __forceinline__ void store_record(float4* nodes, uint32_t rec, v3 lo, v3 hi, int32_t link, uint32_t meta) {
+  __stcg(&nodes[2 * (size_t)rec], make_float4(lo.x, lo.y, lo.z, __int_as_float(link)));
+  __stcg(&nodes[2 * (size_t)rec + 1], make_float4(hi.x, hi.y, hi.z, __uint_as_float(meta)));
+}
+
+// Kernel: bottom-up refit.  One thread per leaf; the second thread to reach a pair owns it.
+// out_root: 6 floats root box + height (as uint bits in out_root_height).
+__global__ void k_refit(uint32_t n, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ meta,
+                        const float4* __restrict__ box_lo, const float4* __restrict__ box_hi, float pad,
+                        const uint32_t* __restrict__ node_parent, const uint32_t* __restrict__ leaf_parent,
+                        uint32_t* __restrict__ flags, uint32_t* __restrict__ heights, float4* __restrict__ nodes,
+                        float* __restrict__ out_root, uint32_t* __restrict__ out_height) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  uint32_t id = vals[s];
+  float4 l4 = box_lo[id], h4 = box_hi[id];
+  v3 lo = mk(l4.x - pad, l4.y - pad, l4.z - pad), hi = mk(h4.x + pad, h4.y + pad, h4.z + pad);
+  const float INF = __int_as_float(0x7f800000);
+  if (n == 1) {
+    store_record(nodes, 0, lo, hi, ~0, meta[id]);
+    store_record(nodes, 1, mk(INF, INF, INF), mk(-INF, -INF, -INF), ~0, meta[id]);
+    out_root[0] = lo.x; out_root[1] = lo.y; out_root[2] = lo.z;
+    out_root[3] = hi.x; out_root[4] = hi.y; out_root[5] = hi.z;
+    *out_height = 1;
+    return;
+  }
+  uint32_t par = leaf_parent[s];
+  store_record(nodes, par, lo, hi, ~(int32_t)s, meta[id]);
+  uint32_t h = 1;  // height of the subtree rooted at the parent pair, counted in pairs
+  for (;;) {
+    uint32_t p = par >> 1;
+    atomicMax(&heights[p], h);
+    __threadfence();
+    if (atomicAdd(&flags[p], 1u) == 0u) return;  // first to arrive: the sibling will finish the pair
+    __threadfence();
+    float4 a0 = __ldcg(&nodes[4 * (size_t)p]), a1 = __ldcg(&nodes[4 * (size_t)p + 1]);
+    float4 b0 = __ldcg(&nodes[4 * (size_t)p + 2]), b1 = __ldcg(&nodes[4 * (size_t)p + 3]);
+    // Aabb::surrounding_box (aabb.rs:74-88)
+    v3 ulo = mk(fminf(a0.x, b0.x), fminf(a0.y, b0.y), fminf(a0.z, b0.z));
+    v3 uhi = mk(fmaxf(a1.x, b1.x), fmaxf(a1.y, b1.y), fmaxf(a1.z, b1.z));
+    h = atomicMax(&heights[p], 0u);
+    if (p == 0) {
+      out_root[0] = ulo.x; out_root[1] = ulo.y; out_root[2] = ulo.z;
+      out_root[3] = uhi.x; out_root[4] = uhi.y; out_root[5] = uhi.z;
+      *out_height = h;
+      return;
+    }
+    par = node_parent[p];
+    store_record(nodes, par, ulo, uhi, (int32_t)p, 0u);
+    h = h + 1;
+  }
+}
+
+template <class T>
+int dev_alloc(rtw_scene* s, T** out, size_t count) {
+  void* p = nullptr;
+  size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return set_error(RTW_ERR_NOMEM, std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+  }
+  s->allocations.push_back(p);
+  s->device_bytes += bytes;
+  *out = (T*)p;
+  return RTW_OK;
+}
+template <class P, class T>
+int dev_upload(rtw_scene* s, P* out, const std::vector<T>& v) {
+  T* p = nullptr;
+  int rc = dev_alloc(s, &p, v.size());
+  if (rc) return rc;
+  if (!v.empty()) RTW_CUDA_TRY(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *out = p;
+  return RTW_OK;
+}
+
+}  // namespace
+
+void free_scene_device(rtw_scene* s) {
+  for (void* p : s->allocations) cudaFree(p);
+  s->allocations.clear();
+  s->device_bytes = 0;
+}
+
+int build_scene_device(rtw_scene* s, float time0, float time1, rtw_build_stats* stats) {
+  const uint32_t n = (uint32_t)s->prim_meta.size();
+  RTW_CUDA_TRY(cudaSetDevice(s->device));
+  cudaEvent_t ev[3];
+  for (auto& e : ev) RTW_CUDA_TRY(cudaEventCreate(&e));
+  RTW_CUDA_TRY(cudaEventRecord(ev[0]));
+
+  // ---- upload -----------------------------------------------------------------------------------
+  SceneDev& d = s->dev;
+  int rc;
+  if ((rc = dev_upload(s, &d.prim_meta, s->prim_meta))) return rc;
+  if ((rc = dev_upload(s, &d.prim_mat, s->prim_mat))) return rc;
+  if ((rc = dev_upload(s, &d.prim_shade, s->prim_shade))) return rc;
+  if ((rc = dev_upload(s, &d.tri_shade, s->tri_shade))) return rc;
+  if ((rc = dev_upload(s, &d.inst_range, s->inst_range))) return rc;
+  if ((rc = dev_upload(s, &d.inst_ops, s->inst_ops))) return rc;
+  if ((rc = dev_upload(s, &d.materials, s->materials))) return rc;
+  if ((rc = dev_upload(s, &d.textures, s->textures))) return rc;
+  if ((rc = dev_upload(s, &d.noise, s->noise_tables))) return rc;
+  if ((rc = dev_upload(s, &d.texels, s->texels))) return rc;
+  d.num_prims = n;
+  d.num_nodes = n > 1 ? n - 1 : 1;
+  d.has_instances = s->inst_range.size() > 1 ? 1u : 0u;
+  RTW_CUDA_TRY(cudaEventRecord(ev[1]));
+
+  // ---- persistent outputs ---------------------------------------------------------------------
+  float4 *d_enc, *d_geom, *d_nodes;
+  int32_t* d_slot_prim;
+  if ((rc = dev_alloc(s, &d_enc, 3 * (size_t)n))) return rc;
+  if ((rc = dev_alloc(s, &d_geom, 3 * (size_t)n))) return rc;
+  if ((rc = dev_alloc(s, &d_nodes, 4 * (size_t)d.num_nodes))) return rc;
+  if ((rc = dev_alloc(s, &d_slot_prim, n))) return rc;
+
+  // ---- scratch ------------------------------------------------------------------------------------
+  const uint32_t sort_blocks = std::min<uint32_t>(std::max<uint32_t>(1, (n + 2047) / 2048), 4u * (uint32_t)s->num_sms);
+  const uint32_t chunk = ((n + sort_blocks - 1) / sort_blocks + SORT_THREADS - 1) / SORT_THREADS * SORT_THREADS;
+  std::vector<void*> scratch;
+  auto salloc = [&](void** p, size_t bytes) -> int {
+    cudaError_t e = cudaMalloc(p, std::max<size_t>(bytes, 16));
+    if (e != cudaSuccess) { cudaGetLastError(); return set_error(RTW_ERR_NOMEM, "cudaMalloc (build scratch) failed"); }
+    scratch.push_back(*p);
+    return RTW_OK;
+  };
+  float4 *d_lo, *d_hi, *d_raw;
+  if ((rc = salloc((void**)&d_raw, sizeof(float4) * 3 * (size_t)n))) return rc;
+  RTW_CUDA_TRY(cudaMemcpy(d_raw, s->raw_geom.data(), sizeof(float4) * 3 * (size_t)n, cudaMemcpyHostToDevice));
+  uint64_t *d_k0, *d_k1;
+  uint32_t *d_v0, *d_v1, *d_hist, *d_bounds, *d_nparent, *d_lparent, *d_flags, *d_heights, *d_height;
+  float* d_root;
+  if ((rc = salloc((void**)&d_lo, sizeof(float4) * n))) return rc;
+  if ((rc = salloc((void**)&d_hi, sizeof(float4) * n))) return rc;
+  if ((rc = salloc((void**)&d_k0, 8ull * n))) return rc;
+  if ((rc = salloc((void**)&d_k1, 8ull * n))) return rc;
+  if ((rc = salloc((void**)&d_v0, 4ull * n))) return rc;
+  if ((rc = salloc((void**)&d_v1, 4ull * n))) return rc;
+  if ((rc = salloc((void**)&d_hist, 4ull * 256 * sort_blocks))) return rc;
+  if ((rc = salloc((void**)&d_bounds, 4 * 8))) return rc;
+  if ((rc = salloc((void**)&d_nparent, 4ull * n))) return rc;
+  if ((rc = salloc((void**)&d_lparent, 4ull * n))) return rc;
+  if ((rc = salloc((void**)&d_flags, 4ull * n))) return rc;
+  if ((rc = salloc((void**)&d_heights, 4ull * n))) return rc;
+  if ((rc = salloc((void**)&d_root, 4 * 8))) return rc;
+  d_height = (uint32_t*)(d_root + 6);
+
+  const uint32_t T = 256, G = (n + T - 1) / T;
+  k_prim_setup<<<G, T>>>(n, d_raw, d.prim_meta, d.inst_range, d.inst_ops, time0, time1, d_enc, d_lo, d_hi);
+  {
+    uint32_t init[8] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u, 0u, 0u, 0u};
+    RTW_CUDA_TRY(cudaMemcpy(d_bounds, init, sizeof(init), cudaMemcpyHostToDevice));
+  }
+  k_bounds<<<std::min<uint32_t>(G, 4u * (uint32_t)s->num_sms), T>>>(n, d_lo, d_hi, d_bounds);
+  k_morton<<<G, T>>>(n, d_lo, d_hi, d_bounds, d_k0, d_v0);
+  for (int pass = 0; pass < 8; ++pass) {
+    int shift = 8 * pass;
+    k_sort_hist<<<sort_blocks, SORT_THREADS>>>(n, chunk, d_k0, shift, d_hist);
+    k_sort_scan<<<1, 1024>>>(256 * sort_blocks, d_hist);
+    k_sort_scatter<<<sort_blocks, SORT_THREADS>>>(n, chunk, d_k0, d_v0, d_k1, d_v1, shift, d_hist);
+    std::swap(d_k0, d_k1);
+    std::swap(d_v0, d_v1);
+  }
+  k_emit_leaves<<<G, T>>>(n, d_v0, d_enc, d_geom, d_slot_prim);
+  RTW_CUDA_TRY(cudaMemset(d_flags, 0, 4ull * n));
+  RTW_CUDA_TRY(cudaMemset(d_heights, 0, 4ull * n));
+  if (n > 1) k_karras<<<G, T>>>((int)n, d_k0, d_nparent, d_lparent);
+  uint32_t h_bounds[8];
+  RTW_CUDA_TRY(cudaMemcpy(h_bounds, d_bounds, sizeof(h_bounds), cudaMemcpyDeviceToHost));
+  const float amax = ord2f(h_bounds[6]);
+  const float pad = amax * (1.0f / 1048576.0f);
+  k_refit<<<G, T>>>(n, d_v0, d.prim_meta, d_lo, d_hi, pad, d_nparent, d_lparent, d_flags, d_heights, d_nodes, d_root,
+                    d_height);
+  RTW_CUDA_TRY(cudaGetLastError());
+  RTW_CUDA_TRY(cudaEventRecord(ev[2]));
+  RTW_CUDA_TRY(cudaEventSynchronize(ev[2]));
+  float h_root[8];
+  RTW_CUDA_TRY(cudaMemcpy(h_root, d_root, sizeof(h_root), cudaMemcpyDeviceToHost));
+  memcpy(s->root_box, h_root, 6 * sizeof(float));
+  memcpy(&s->bvh_height, &h_root[6], 4);
+  for (void* p : scratch) cudaFree(p);
+
+  d.nodes = d_nodes;
+  d.geom = d_geom;
+  d.raw_geom = d_enc;
+  d.slot_prim = d_slot_prim;
+
+  float ms_up = 0.f, ms_build = 0.f;
+  cudaEventElapsedTime(&ms_up, ev[0], ev[1]);
+  cudaEventElapsedTime(&ms_build, ev[1], ev[2]);
+  for (auto& e : ev) cudaEventDestroy(e);
+  if (s->bvh_height + 2 > RTW_STACK_SIZE)
+    return set_error(RTW_ERR_UNSUPPORTED, "LBVH deeper than the traversal stack (" + std::to_string(s->bvh_height) + ")");
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    stats->num_prims = n;
+    stats->num_nodes = d.num_nodes;
+    stats->max_depth = s->bvh_height;
+    stats->num_instances = (uint32_t)s->inst_range.size();
+    stats->ms_build = ms_build;
+    stats->ms_upload = ms_up;
+    stats->device_bytes = s->device_bytes;
+  }
+  return RTW_OK;
+}
+
+}  // namespace rtw

@@ -1,0 +1,543 @@
+// Wavefront path tracer: the GPU form of Raytracer::render (lib.rs:57-117).
+//
+//   pool of P path slots (SoA in HBM) ──► k_wave_traverse ──► k_wave_shade ──► next queue
+//
+// * A slot owns one WORK ITEM = (pixel, sample slice): it runs the samples of that slice one after
+//   the other (lib.rs:83-88), adding each path's radiance to a running sum in sample order, writes
+//   the slice sum when done and pulls the next item from a global cursor (path regeneration), so
+//   the pool stays full until the frame runs dry.  Slices of a pixel are added in slice order by
+//   k_wave_resolve.  Every float addition therefore happens in an order fixed by (spp, slices)
+//   alone — the image is bit-reproducible for any pool size, GPU count or scheduling.
+// * sample_ray's recursion (lib.rs:97-117) is run in its iterative form L += T*e; T *= a
+//   (SURVEY.md §8 a3); one iteration of the wavefront = one path segment per live slot.
+// * Both kernels are persistent: grid = SMs x resident blocks, warps pull 32 queue entries at a
+//   time from a device-side cursor, so no launch parameter depends on the live count and the host
+//   only synchronises every few iterations to learn whether the queue is empty.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "rtw_scene.cuh"
+#include "rtw_traverse.cuh"
+
+namespace rtw {
+
+namespace {
+
+struct WaveCtl {
+  unsigned long long item_cursor;
+  unsigned long long segments;
+  unsigned long long paths;
+  unsigned long long pairs;
+  unsigned long long prims;
+  uint32_t count[2];
+  uint32_t cursor_traverse;
+  uint32_t cursor_shade;
+  uint32_t pad[2];
+};
+
+struct WaveDev {
+  float4* ray_o;    // origin.xyz, time
+  float4* ray_d;    // direction.xyz, -
+  int2* hit;        // primitive slot (or -1), t bits
+  float4* thr;      // throughput T.rgb
+  float4* sum;      // running slice sum rgb
+  uint4* state;     // pixel index (row*w+col), sample, sample_end, bounce | slice << 8
+  uint32_t* queue[2];
+  float4* partial;  // [slices][w*h] slice sums (slices > 1)
+  WaveCtl* ctl;
+};
+
+struct FrameDev {
+  CameraDev cam;
+  v3 background;
+  uint32_t width, height;
+  uint32_t max_depth;
+  uint32_t sample_begin, nsamp, slices;
+  uint32_t tile_size, tiles_x, tiles_total, part_rank, part_count;
+  uint32_t seed_lo, seed_hi;
+  unsigned long long pix_per_slice;  // owned tiles * tile_size^2 (includes out-of-image padding)
+  unsigned long long n_items;
+  uint32_t pool;
+};
+
+struct WaveHost {
+  WaveDev dev{};
+  std::vector<void*> allocs;
+  uint32_t pool = 0;
+  size_t partial_elems = 0;
+  WaveCtl* pinned_ctl = nullptr;
+  int blocks_traverse = 0, blocks_traverse_count = 0, blocks_shade = 0;
+};
+
+// ---- work items ---------------------------------------------------------------------------------
+struct Item {
+  uint32_t pixel;  // row*w + col   (row = bottom-up like Pixel.row, lib.rs:58)
+  uint32_t sample, sample_end, slice;
+};
+
+__device__ __forceinline__ bool decode_item(const FrameDev& f, unsigned long long n, Item& it) {
+  uint32_t k = (uint32_t)(n / f.pix_per_slice);
+  unsigned long long q = n % f.pix_per_slice;
+  uint32_t tsq = f.tile_size * f.tile_size;
+  uint32_t tile_local = (uint32_t)(q / tsq), within = (uint32_t)(q % tsq);
+  unsigned long long tile = (unsigned long long)tile_local * f.part_count + f.part_rank;
+  if (tile >= f.tiles_total) return false;
+  uint32_t tx = (uint32_t)(tile % f.tiles_x), ty = (uint32_t)(tile / f.tiles_x);
+  uint32_t x = tx * f.tile_size + within % f.tile_size;
+  uint32_t y_top = ty * f.tile_size + within / f.tile_size;
+  if (x >= f.width || y_top >= f.height) return false;
+  uint32_t row = f.height - 1 - y_top;
+  it.pixel = row * f.width + x;
+  it.slice = k;
+  it.sample = f.sample_begin + (uint32_t)(((unsigned long long)f.nsamp * k) / f.slices);
+  it.sample_end = f.sample_begin + (uint32_t)(((unsigned long long)f.nsamp * (k + 1)) / f.slices);
+  return it.sample_end > it.sample;
+}
+
+// Warp-cooperative fetch: every lane with `need` gets a valid item or learns that none are left.
+// Must be called by all 32 lanes.
+__device__ __forceinline__ bool fetch_item(const FrameDev& f, WaveCtl* ctl, bool need, Item& it) {
+  const uint32_t lane = threadIdx.x & 31;
+  bool got = false;
+  for (;;) {
+    uint32_t m = __ballot_sync(0xffffffffu, need && !got);
+    if (m == 0) break;
+    unsigned long long base = 0;
+    if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(&ctl->item_cursor, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (base >= f.n_items) break;  // exhausted (cursor may overshoot; harmless)
+    if (need && !got) {
+      unsigned long long n = base + __popc(m & ((1u << lane) - 1u));
+      if (n < f.n_items) got = decode_item(f, n, it);
+      else need = false;
+    }
+  }
+  return got;
+}
+
+// lib.rs:84-86: start sample `it.sample` of the item's pixel.
+__device__ __forceinline__ void start_path(const FrameDev& f, const WaveDev& w, uint32_t slot, const Item& it) {
+  Rng rng;
+  rng.begin(((uint64_t)f.seed_hi << 32) | f.seed_lo, it.pixel, it.sample, 0);
+  uint32_t row = it.pixel / f.width, col = it.pixel % f.width;
+  v3 o, d;
+  float time;
+  camera_ray(f.cam, f.width, f.height, row, col, rng, o, d, time);
+  w.ray_o[slot] = make_float4(o.x, o.y, o.z, time);
+  w.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.f);
+  w.thr[slot] = make_float4(1.f, 1.f, 1.f, 0.f);
+  w.state[slot] = make_uint4(it.pixel, it.sample, it.sample_end, it.slice << 8);
+}
+
+__device__ __forceinline__ void queue_push(uint32_t* queue, uint32_t* count, bool alive, uint32_t slot) {
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t m = __ballot_sync(0xffffffffu, alive);
+  if (m == 0) return;
+  uint32_t base = 0;
+  if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(count, (uint32_t)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+  if (alive) queue[base + __popc(m & ((1u << lane) - 1u))] = slot;
+}
+
+__global__ void k_wave_init(SceneDev sc, FrameDev f, WaveDev w) {
+  uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;  // block = 128 threads: whole warps reach the ballots
+  Item it;
+  bool got = fetch_item(f, w.ctl, slot < f.pool, it);
+  if (got) {
+    start_path(f, w, slot, it);
+    w.sum[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  uint32_t m = __ballot_sync(0xffffffffu, got);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(&w.ctl->paths, (unsigned long long)__popc(m));
+  queue_push(w.queue[0], &w.ctl->count[0], got, slot);
+}
+
+// ---- traversal -----------------------------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_wave_traverse(SceneDev sc, WaveDev w, uint32_t parity) {
+  WaveCtl* ctl = w.ctl;
+  const uint32_t count = ctl->count[parity];
+  const uint32_t* __restrict__ queue = w.queue[parity];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    ctl->cursor_shade = 0;        // consumed by the shade kernel that follows
+    ctl->count[parity ^ 1] = 0;   // the queue that shade kernel fills (its old content was consumed last iteration)
+    ctl->segments += count;
+  }
+  const uint32_t lane = threadIdx.x & 31;
+  TraverseCounters cnt;
+  for (;;) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&ctl->cursor_traverse, 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= count) break;
+    uint32_t i = base + lane;
+    if (i < count) {
+      uint32_t slot = queue[i];
+      float4 o4 = w.ray_o[slot], d4 = w.ray_d[slot];
+      int32_t hslot;
+      float t;
+      uint32_t meta;
+      // lib.rs:102: world.hit(r, 0.001, f32::INFINITY)
+      traverse_closest<COUNT>(sc, mk(o4.x, o4.y, o4.z), mk(d4.x, d4.y, d4.z), o4.w, 0.001f, __int_as_float(0x7f800000),
+                              hslot, t, meta, cnt);
+      w.hit[slot] = make_int2(hslot, __float_as_int(t));
+    }
+  }
+  if (COUNT) {
+    uint32_t p = cnt.pairs, q = cnt.prims;
+    for (int off = 16; off > 0; off >>= 1) {
+      p += __shfl_xor_sync(0xffffffffu, p, off);
+      q += __shfl_xor_sync(0xffffffffu, q, off);
+    }
+    if (lane == 0) {
+      atomicAdd(&ctl->pairs, (unsigned long long)p);
+      atomicAdd(&ctl->prims, (unsigned long long)q);
+    }
+  }
+}
+
+// ---- shade + scatter + regenerate -----------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_wave_shade(SceneDev sc, FrameDev f, WaveDev w, float* __restrict__ accum,
+                                                    uint32_t parity) {
+  WaveCtl* ctl = w.ctl;
+  const uint32_t count = ctl->count[parity];
+  const uint32_t* __restrict__ queue = w.queue[parity];
+  uint32_t* next_queue = w.queue[parity ^ 1];
+  uint32_t* next_count = &ctl->count[parity ^ 1];
+  if (blockIdx.x == 0 && threadIdx.x == 0) ctl->cursor_traverse = 0;  // for the next traversal launch
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t seed = ((uint64_t)f.seed_hi << 32) | f.seed_lo;
+  uint32_t new_paths = 0;
+  for (;;) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(&ctl->cursor_shade, 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= count) break;
+    const uint32_t i = base + lane;
+    const bool active = i < count;
+    uint32_t slot = 0;
+    bool alive = false;       // slot continues into the next iteration
+    bool need_item = false;   // slot finished its item and wants another
+    Item it;
+    if (active) {
+      slot = queue[i];
+      const int2 h = w.hit[slot];
+      const float4 o4 = w.ray_o[slot], d4 = w.ray_d[slot];
+      const float4 T4 = w.thr[slot];
+      uint4 st = w.state[slot];
+      v3 T = mk(T4.x, T4.y, T4.z);
+      uint32_t bounce = st.w & 0xffu;
+      bool terminated;
+      v3 L = mk(0.f, 0.f, 0.f);
+      if (h.x < 0) {  // lib.rs:102-105: miss -> background
+        L = T * f.background;
+        terminated = true;
+      } else {
+        const int32_t id = sc.slot_prim[h.x];
+        const uint32_t meta = sc.prim_meta[id];
+        const MaterialRec m = sc.materials[sc.prim_mat[id]];
+        const v3 o = mk(o4.x, o4.y, o4.z), d = mk(d4.x, d4.y, d4.z);
+        const bool need_uv = (m.type == MT_LAMBERTIAN || m.type == MT_DIFFUSE_LIGHT) && texture_needs_uv(sc, m.tex);
+        HitRec rec;
+        finalize_hit(sc, meta & 7u, meta >> RTW_META_TYPE_BITS, sc.geom + 3 * (size_t)h.x, sc.prim_shade[id], o, d, o4.w,
+                     __int_as_float(h.y), need_uv, rec);
+        const v3 emitted = material_emitted(sc, m, rec);  // lib.rs:107-109
+        Rng rng;
+        rng.begin(seed, st.x, st.y, bounce + 1);
+        v3 att, out_dir;
+        if (!material_scatter(sc, m, d, rec, rng, att, out_dir)) {  // lib.rs:111-114
+          L = T * emitted;
+          terminated = true;
+        } else {
+          // L += T*emitted with emitted == 0 for every scattering material: exact no-op
+          T = T * att;  // lib.rs:116
+          bounce += 1;
+          terminated = bounce >= f.max_depth;  // lib.rs:98-100: depth exhausted -> black
+          if (!terminated) {
+            w.ray_o[slot] = make_float4(rec.p.x, rec.p.y, rec.p.z, o4.w);
+            w.ray_d[slot] = make_float4(out_dir.x, out_dir.y, out_dir.z, 0.f);
+            w.thr[slot] = make_float4(T.x, T.y, T.z, 0.f);
+            w.state[slot] = make_uint4(st.x, st.y, st.z, (st.w & ~0xffu) | bounce);
+            alive = true;
+          }
+        }
+      }
+      if (terminated) {
+        float4 s4 = w.sum[slot];
+        v3 sum = mk(s4.x, s4.y, s4.z) + L;  // lib.rs:87: pixel_color += sample_ray(..)
+        if (st.y + 1 < st.z) {  // next sample of the same item
+          w.sum[slot] = make_float4(sum.x, sum.y, sum.z, 0.f);
+          it.pixel = st.x; it.sample = st.y + 1; it.sample_end = st.z; it.slice = st.w >> 8;
+          start_path(f, w, slot, it);
+          new_paths++;
+          alive = true;
+        } else {  // item done: publish the slice sum
+          uint32_t row = st.x / f.width, col = st.x % f.width;
+          size_t pix = (size_t)(f.height - 1 - row) * f.width + col;
+          if (f.slices == 1) {
+            accum[3 * pix] = sum.x; accum[3 * pix + 1] = sum.y; accum[3 * pix + 2] = sum.z;
+          } else {
+            w.partial[(size_t)(st.w >> 8) * f.width * f.height + pix] = make_float4(sum.x, sum.y, sum.z, 0.f);
+          }
+          need_item = true;
+        }
+      }
+    }
+    if (fetch_item(f, ctl, need_item, it)) {
+      w.sum[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+      start_path(f, w, slot, it);
+      new_paths++;
+      alive = true;
+    }
+    queue_push(next_queue, next_count, alive, slot);
+  }
+  for (int off = 16; off > 0; off >>= 1) new_paths += __shfl_xor_sync(0xffffffffu, new_paths, off);
+  if (lane == 0 && new_paths) atomicAdd(&ctl->paths, (unsigned long long)new_paths);
+}
+
+// pixel_color = sum over slices, in slice order; pixels of other partitions = 0
+__global__ void k_wave_resolve(FrameDev f, const float4* __restrict__ partial, float* __restrict__ accum) {
+  size_t npix = (size_t)f.width * f.height;
+  for (size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += (size_t)gridDim.x * blockDim.x) {
+    uint32_t x = (uint32_t)(pix % f.width), y_top = (uint32_t)(pix / f.width);
+    uint32_t tile = (y_top / f.tile_size) * f.tiles_x + (x / f.tile_size);
+    v3 acc = mk(0.f, 0.f, 0.f);
+    if (tile % f.part_count == f.part_rank) {
+      for (uint32_t k = 0; k < f.slices; ++k) {
+        float4 s = partial[(size_t)k * npix + pix];
+        acc = acc + mk(s.x, s.y, s.z);
+      }
+    }
+    accum[3 * pix] = acc.x; accum[3 * pix + 1] = acc.y; accum[3 * pix + 2] = acc.z;
+  }
+}
+
+// console_app/src/main.rs:73-86
+__global__ void k_resolve_rgb8(const float* __restrict__ accum, size_t n, float scale, uint8_t* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float c = sqrtf(scale * accum[i]);
+    float cl = c;
+    if (cl < 0.0f) cl = 0.0f;
+    if (cl > 0.999f) cl = 0.999f;
+    float v = 255.999f * cl;
+    uint32_t b = (v != v) ? 0u : __float2uint_rz(v);  // `as u8`: saturating, NaN -> 0
+    out[i] = (uint8_t)min(b, 255u);
+  }
+}
+
+template <class T>
+int wave_alloc(WaveHost* wh, T** out, size_t count) {
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return set_error(RTW_ERR_NOMEM, std::string("cudaMalloc (wavefront state) failed: ") + cudaGetErrorString(e));
+  }
+  wh->allocs.push_back(p);
+  *out = (T*)p;
+  return RTW_OK;
+}
+
+void wave_release(WaveHost* wh) {
+  for (void* p : wh->allocs) cudaFree(p);
+  wh->allocs.clear();
+  wh->pool = 0;
+  wh->partial_elems = 0;
+}
+
+}  // namespace
+
+void free_wave(rtw_scene* s) {
+  WaveHost* wh = (WaveHost*)s->wave;
+  if (!wh) return;
+  wave_release(wh);
+  if (wh->pinned_ctl) cudaFreeHost(wh->pinned_ctl);
+  delete wh;
+  s->wave = nullptr;
+}
+
+int resolve_rgb8_device(const float* d_accum, size_t n, uint32_t spp, uint8_t* d_rgb8, cudaStream_t st) {
+  if (n == 0) return RTW_OK;
+  float scale = 1.0f / (float)spp;
+  uint32_t blocks = (uint32_t)std::min<size_t>((n + 255) / 256, 65535);
+  k_resolve_rgb8<<<blocks, 256, 0, st>>>(d_accum, n, scale, d_rgb8);
+  RTW_CUDA_TRY(cudaGetLastError());
+  return RTW_OK;
+}
+
+int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* p, float* d_accum, cudaStream_t st,
+                  rtw_render_stats* stats) {
+  RTW_CUDA_TRY(cudaSetDevice(s->device));
+  if (p->width < 2 || p->height < 2) return set_error(RTW_ERR_INVALID, "render: width and height must be >= 2");
+  if ((uint64_t)p->width * p->height > 0xFFFFFFFFull) return set_error(RTW_ERR_INVALID, "render: image too large");
+  uint32_t s0 = p->sample_begin, s1 = p->sample_end;
+  if (s0 == 0 && s1 == 0) s1 = p->spp;
+  if (s1 < s0) return set_error(RTW_ERR_INVALID, "render: sample_end < sample_begin");
+  const uint32_t nsamp = s1 - s0;
+  const size_t npix = (size_t)p->width * p->height;
+
+  FrameDev f;
+  memset(&f, 0, sizeof(f));
+  auto V = [](const float* a) { return mk(a[0], a[1], a[2]); };
+  f.cam.origin = V(cam->origin);
+  f.cam.lower_left_corner = V(cam->lower_left_corner);
+  f.cam.horizontal = V(cam->horizontal);
+  f.cam.vertical = V(cam->vertical);
+  f.cam.u = V(cam->u);
+  f.cam.v = V(cam->v);
+  f.cam.lens_radius = cam->lens_radius;
+  f.cam.time0 = cam->time0;
+  f.cam.time1 = cam->time1;
+  f.background = V(p->background);
+  f.width = p->width;
+  f.height = p->height;
+  f.max_depth = p->max_depth ? p->max_depth : 50;
+  if (f.max_depth > 255) return set_error(RTW_ERR_INVALID, "render: max_depth must be <= 255");
+  f.sample_begin = s0;
+  f.nsamp = nsamp;
+  f.tile_size = p->tile_size ? p->tile_size : 32;
+  f.tiles_x = (p->width + f.tile_size - 1) / f.tile_size;
+  const uint32_t tiles_y = (p->height + f.tile_size - 1) / f.tile_size;
+  f.tiles_total = f.tiles_x * tiles_y;
+  f.part_count = p->part_count ? p->part_count : 1;
+  f.part_rank = p->part_rank;
+  if (f.part_rank >= f.part_count) return set_error(RTW_ERR_INVALID, "render: part_rank >= part_count");
+  f.seed_lo = (uint32_t)p->seed;
+  f.seed_hi = (uint32_t)(p->seed >> 32);
+  const uint32_t owned_tiles = f.tiles_total > f.part_rank ? (f.tiles_total - f.part_rank + f.part_count - 1) / f.part_count : 0;
+  f.pix_per_slice = (unsigned long long)owned_tiles * f.tile_size * f.tile_size;
+
+  uint32_t pool = p->pool_size ? p->pool_size : (1u << 20);
+  pool = (pool + 31u) & ~31u;
+  uint32_t slices = p->slices;
+  if (slices == 0) {  // enough items that the last ones to finish are a small fraction of the frame
+    unsigned long long want = 16ull * pool;
+    unsigned long long per = std::max<unsigned long long>(f.pix_per_slice, 1);
+    slices = (uint32_t)std::min<unsigned long long>((want + per - 1) / per, 64ull);
+  }
+  slices = std::max(1u, std::min(slices, std::max(nsamp, 1u)));
+  if (slices > 0xFFFFFFu) return set_error(RTW_ERR_INVALID, "render: too many slices");
+  f.slices = slices;
+  f.n_items = (nsamp == 0) ? 0ull : f.pix_per_slice * slices;
+  pool = (uint32_t)std::min<unsigned long long>(pool, std::max<unsigned long long>((f.n_items + 31ull) & ~31ull, 32ull));
+  f.pool = pool;
+
+  // ---- scratch (kept on the scene between calls) -------------------------------------------------
+  WaveHost* wh = (WaveHost*)s->wave;
+  if (!wh) {
+    wh = new WaveHost();
+    s->wave = wh;
+    RTW_CUDA_TRY(cudaMallocHost((void**)&wh->pinned_ctl, sizeof(WaveCtl)));
+    int nb = 0;
+    RTW_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wave_traverse<false>, 128, 0));
+    wh->blocks_traverse = std::max(nb, 1) * s->num_sms;
+    RTW_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wave_traverse<true>, 128, 0));
+    wh->blocks_traverse_count = std::max(nb, 1) * s->num_sms;
+    RTW_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wave_shade, 128, 0));
+    wh->blocks_shade = std::max(nb, 1) * s->num_sms;
+  }
+  const size_t partial_elems = slices > 1 ? (size_t)slices * npix : 0;
+  if (wh->pool != pool || wh->partial_elems < partial_elems) {
+    wave_release(wh);
+    int rc;
+    WaveDev& w = wh->dev;
+    if ((rc = wave_alloc(wh, &w.ray_o, pool))) return rc;
+    if ((rc = wave_alloc(wh, &w.ray_d, pool))) return rc;
+    if ((rc = wave_alloc(wh, &w.hit, pool))) return rc;
+    if ((rc = wave_alloc(wh, &w.thr, pool))) return rc;
+    if ((rc = wave_alloc(wh, &w.sum, pool))) return rc;
+    if ((rc = wave_alloc(wh, &w.state, pool))) return rc;
+    if ((rc = wave_alloc(wh, &w.queue[0], pool))) return rc;
+    if ((rc = wave_alloc(wh, &w.queue[1], pool))) return rc;
+    if ((rc = wave_alloc(wh, &w.partial, partial_elems))) return rc;
+    if ((rc = wave_alloc(wh, &w.ctl, 1))) return rc;
+    wh->pool = pool;
+    wh->partial_elems = partial_elems;
+  }
+  WaveDev& w = wh->dev;
+
+  const bool count_trav = (p->flags & RTW_RENDER_COUNT_TRAVERSAL) != 0;
+  const bool time_kernels = (p->flags & 2u) != 0;
+  cudaEvent_t ev_begin, ev_end;
+  RTW_CUDA_TRY(cudaEventCreate(&ev_begin));
+  RTW_CUDA_TRY(cudaEventCreate(&ev_end));
+  std::vector<cudaEvent_t> kev;  // begin/end pairs: traverse, shade, traverse, shade ...
+  uint32_t launches = 0, iterations = 0;
+
+  RTW_CUDA_TRY(cudaEventRecord(ev_begin, st));
+  RTW_CUDA_TRY(cudaMemsetAsync(w.ctl, 0, sizeof(WaveCtl), st));
+  if (slices == 1) RTW_CUDA_TRY(cudaMemsetAsync(d_accum, 0, npix * 3 * sizeof(float), st));
+  if (f.n_items > 0) {
+    k_wave_init<<<(pool + 127) / 128, 128, 0, st>>>(s->dev, f, w);
+    launches++;
+    uint32_t parity = 0;
+    const int batch = 8;
+    for (;;) {
+      for (int b = 0; b < batch; ++b) {
+        if (time_kernels) {
+          cudaEvent_t e4[4];
+          for (auto& e : e4) { RTW_CUDA_TRY(cudaEventCreate(&e)); kev.push_back(e); }
+          RTW_CUDA_TRY(cudaEventRecord(e4[0], st));
+        }
+        if (count_trav)
+          k_wave_traverse<true><<<wh->blocks_traverse_count, 128, 0, st>>>(s->dev, w, parity);
+        else
+          k_wave_traverse<false><<<wh->blocks_traverse, 128, 0, st>>>(s->dev, w, parity);
+        if (time_kernels) {
+          RTW_CUDA_TRY(cudaEventRecord(kev[kev.size() - 3], st));
+          RTW_CUDA_TRY(cudaEventRecord(kev[kev.size() - 2], st));
+        }
+        k_wave_shade<<<wh->blocks_shade, 128, 0, st>>>(s->dev, f, w, d_accum, parity);
+        if (time_kernels) RTW_CUDA_TRY(cudaEventRecord(kev[kev.size() - 1], st));
+        parity ^= 1;
+        launches += 2;
+        iterations++;
+      }
+      RTW_CUDA_TRY(cudaMemcpyAsync(wh->pinned_ctl, w.ctl, sizeof(WaveCtl), cudaMemcpyDeviceToHost, st));
+      RTW_CUDA_TRY(cudaStreamSynchronize(st));
+      if (wh->pinned_ctl->count[parity] == 0) break;
+    }
+  }
+  if (slices > 1 || f.n_items == 0) {
+    if (f.n_items == 0 && slices > 1) RTW_CUDA_TRY(cudaMemsetAsync(w.partial, 0, partial_elems * sizeof(float4), st));
+    if (slices > 1) {
+      k_wave_resolve<<<std::min<uint32_t>((uint32_t)((npix + 255) / 256), 8u * (uint32_t)s->num_sms), 256, 0, st>>>(f, w.partial, d_accum);
+      launches++;
+    }
+  }
+  RTW_CUDA_TRY(cudaGetLastError());
+  RTW_CUDA_TRY(cudaEventRecord(ev_end, st));
+  RTW_CUDA_TRY(cudaMemcpyAsync(wh->pinned_ctl, w.ctl, sizeof(WaveCtl), cudaMemcpyDeviceToHost, st));
+  RTW_CUDA_TRY(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ev_begin, ev_end);
+  cudaEventDestroy(ev_begin);
+  cudaEventDestroy(ev_end);
+  float ms_t = 0.f, ms_s = 0.f;
+  for (size_t i = 0; i + 3 < kev.size(); i += 4) {
+    float a = 0.f, b = 0.f;
+    cudaEventElapsedTime(&a, kev[i], kev[i + 1]);
+    cudaEventElapsedTime(&b, kev[i + 2], kev[i + 3]);
+    ms_t += a;
+    ms_s += b;
+  }
+  for (auto& e : kev) cudaEventDestroy(e);
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    stats->segments = wh->pinned_ctl->segments;
+    stats->paths = wh->pinned_ctl->paths;
+    stats->node_visits = wh->pinned_ctl->pairs;
+    stats->prim_tests = wh->pinned_ctl->prims;
+    stats->iterations = iterations;
+    stats->launches = launches;
+    stats->pool_size = pool;
+    stats->slices = slices;
+    stats->ms_render = ms;
+    stats->ms_traverse = ms_t;
+    stats->ms_shade = ms_s;
+  }
+  return RTW_OK;
+}
+
+}  // namespace rtw

@@ -1,0 +1,127 @@
+// Closest-hit traversal of the pair-layout LBVH (rtw_bvh.cu): the GPU replacement of
+//   world.hit(r, t_min, t_max)  =  list rule (hittable/mod.rs:57-69) over BvhNode::hit (bvh.rs:101-120)
+//                                   over Aabb::hit (aabb.rs:23-48) over the primitives' hit().
+//
+// Result contract (exceptions 1-2): the primitive with the smallest accepted t;
+// among primitives with bit-equal t the one with the HIGHEST canonical id — exactly what the
+// reference's flat list in canonical order returns ("last tested wins", t == t_max is accepted).
+#pragma once
+#include "rtw_device.cuh"
+
+namespace rtw {
+
+// Slab test of one child record against the ray: aabb.rs:23-48 with (a) the reciprocal hoisted out
+// of the node loop (1/d is the same value every time), (b) a NON-strict reject (the reference
+// rejects t_max <= t_min; we keep t_max == t_min so that exact-t ties are still visited) and
+// (c) the exit distance inflated by 4 ulp, so that rounding in the slab arithmetic can only make
+// the test more conservative than the exact-arithmetic one.  NaNs from 0*inf are dropped by
+// fminf/fmaxf exactly like Rust's f32::min/max do.
+__device__ __forceinline__ bool slab(float4 lo, float4 hi, v3 o, v3 inv, float t_min, float t_max, float& t_near) {
+  float t0 = (lo.x - o.x) * inv.x, t1 = (hi.x - o.x) * inv.x;
+  float tn = inv.x < 0.0f ? t1 : t0, tf = inv.x < 0.0f ? t0 : t1;
+  t_min = fmaxf(tn, t_min);
+  t_max = fminf(tf, t_max);
+  t0 = (lo.y - o.y) * inv.y; t1 = (hi.y - o.y) * inv.y;
+  tn = inv.y < 0.0f ? t1 : t0; tf = inv.y < 0.0f ? t0 : t1;
+  t_min = fmaxf(tn, t_min);
+  t_max = fminf(tf, t_max);
+  t0 = (lo.z - o.z) * inv.z; t1 = (hi.z - o.z) * inv.z;
+  tn = inv.z < 0.0f ? t1 : t0; tf = inv.z < 0.0f ? t0 : t1;
+  t_min = fmaxf(tn, t_min);
+  t_max = fminf(tf, t_max);
+  t_near = t_min;
+  float t_far = __fmaf_rn(fabsf(t_max), 4.76837158e-7f, t_max);
+  return t_min <= t_far;
+}
+
+struct TraverseCounters {
+  uint32_t pairs = 0;
+  uint32_t prims = 0;
+};
+
+template <bool COUNT>
+__device__ __forceinline__ void traverse_closest(const SceneDev& sc, v3 o, v3 d, float time, float t_min, float t_max,
+                                                 int32_t& best_slot, float& best_t, uint32_t& best_meta,
+                                                 TraverseCounters& cnt) {
+  best_slot = -1;
+  best_t = t_max;
+  best_meta = 0;
+  int32_t best_id = -2;  // canonical id of best_slot, fetched lazily (only ties need it)
+  const v3 inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);  // aabb.rs:29
+  int2 stack[RTW_STACK_SIZE];
+  int sp = 0;
+  v3 oi = o, di = d;
+  uint32_t cur_inst = 0;
+  int32_t link = 0;
+  uint32_t meta = 0;
+  for (;;) {
+    if (link >= 0) {
+      const float4* __restrict__ n = sc.nodes + 4 * (size_t)link;
+      float4 l0 = __ldg(n), l1 = __ldg(n + 1), r0 = __ldg(n + 2), r1 = __ldg(n + 3);
+      if (COUNT) cnt.pairs++;
+      float tl, tr;
+      bool hl = slab(l0, l1, o, inv, t_min, best_t, tl);
+      bool hr = slab(r0, r1, o, inv, t_min, best_t, tr);
+      if (hl && hr) {
+        bool left_first = tl <= tr;
+        int2 far_e = left_first ? make_int2(__float_as_int(r0.w), __float_as_int(r1.w))
+                                : make_int2(__float_as_int(l0.w), __float_as_int(l1.w));
+        stack[sp++] = far_e;
+        link = left_first ? __float_as_int(l0.w) : __float_as_int(r0.w);
+        meta = left_first ? __float_as_uint(l1.w) : __float_as_uint(r1.w);
+        continue;
+      }
+      if (hl) { link = __float_as_int(l0.w); meta = __float_as_uint(l1.w); continue; }
+      if (hr) { link = __float_as_int(r0.w); meta = __float_as_uint(r1.w); continue; }
+    } else {
+      const uint32_t slot = (uint32_t)(~link);
+      const uint32_t type = meta & 7u, inst = meta >> RTW_META_TYPE_BITS;
+      if (inst != cur_inst) {
+        oi = o; di = d;
+        if (inst != 0) ray_to_instance(sc, inst, oi, di);
+        cur_inst = inst;
+      }
+      if (COUNT) cnt.prims++;
+      float t;
+      if (prim_t(type, sc.geom + 3 * (size_t)slot, oi, di, time, t_min, best_t, t)) {
+        if (best_slot < 0 || t < best_t) {
+          best_t = t; best_slot = (int32_t)slot; best_meta = meta; best_id = -2;
+        } else {  // t == best_t: the later primitive of the canonical order wins (hittable/mod.rs:61-66)
+          if (best_id == -2) best_id = __ldg(sc.slot_prim + best_slot);
+          int32_t id = __ldg(sc.slot_prim + slot);
+          if (id > best_id) { best_slot = (int32_t)slot; best_meta = meta; best_id = id; }
+        }
+      }
+    }
+    if (sp == 0) break;
+    int2 e = stack[--sp];
+    link = e.x;
+    meta = (uint32_t)e.y;
+  }
+}
+
+// Every primitive in canonical order: hittable/mod.rs:57-69 literally (closest_so_far shrink,
+// later primitive wins on equal t).  The debug / ground-truth path of rtw_trace_closest.
+__device__ __forceinline__ void brute_closest(const SceneDev& sc, v3 o, v3 d, float time, float t_min, float t_max,
+                                              int32_t& best_id, float& best_t, uint32_t& best_meta) {
+  best_id = -1;
+  best_t = t_max;
+  best_meta = 0;
+  v3 oi = o, di = d;
+  uint32_t cur_inst = 0;
+  for (uint32_t id = 0; id < sc.num_prims; ++id) {
+    uint32_t meta = __ldg(sc.prim_meta + id);
+    uint32_t type = meta & 7u, inst = meta >> RTW_META_TYPE_BITS;
+    if (inst != cur_inst) {
+      oi = o; di = d;
+      if (inst != 0) ray_to_instance(sc, inst, oi, di);
+      cur_inst = inst;
+    }
+    float t;
+    if (prim_t(type, sc.raw_geom + 3 * (size_t)id, oi, di, time, t_min, best_t, t)) {
+      best_t = t; best_id = (int32_t)id; best_meta = meta;
+    }
+  }
+}
+
+}  // namespace rtw
