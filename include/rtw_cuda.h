@@ -103,6 +103,8 @@ typedef struct rtw_render_stats {
   uint64_t paths;         /* camera paths started                                          */
   uint64_t node_visits;   /* 64-byte child-pair fetches (only with COUNT_TRAVERSAL)        */
   uint64_t prim_tests;    /* primitive intersection tests (only with COUNT_TRAVERSAL)      */
+  uint64_t prim_bytes;    /* geometry bytes those tests fetched: sphere 16, rect 32,       */
+                          /*   moving sphere / triangle 48 (only with COUNT_TRAVERSAL)     */
   uint32_t iterations;    /* wavefront iterations (one traverse + one shade launch each)   */
   uint32_t launches;      /* kernels launched by this call                                 */
   uint32_t pool_size;     /* slots actually used                                           */

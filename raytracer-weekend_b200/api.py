@@ -55,6 +55,7 @@ class RenderParams(C.Structure):
 
 class RenderStats(C.Structure):
     _fields_ = [("segments", C.c_uint64), ("paths", C.c_uint64), ("node_visits", C.c_uint64), ("prim_tests", C.c_uint64),
+                ("prim_bytes", C.c_uint64),
                 ("iterations", C.c_uint32), ("launches", C.c_uint32), ("pool_size", C.c_uint32), ("slices", C.c_uint32),
                 ("ms_render", C.c_float), ("ms_traverse", C.c_float), ("ms_shade", C.c_float), ("reserved", C.c_float)]
 

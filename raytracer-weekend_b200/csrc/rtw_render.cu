@@ -30,6 +30,7 @@ struct WaveCtl {
   unsigned long long paths;
   unsigned long long pairs;
   unsigned long long prims;
+  unsigned long long prim_bytes;
   uint32_t count[2];
   uint32_t cursor_traverse;
   uint32_t cursor_shade;
@@ -185,14 +186,16 @@ __global__ void __launch_bounds__(128) k_wave_traverse(SceneDev sc, WaveDev w, u
     }
   }
   if (COUNT) {
-    uint32_t p = cnt.pairs, q = cnt.prims;
+    uint32_t p = cnt.pairs, q = cnt.prims, r = cnt.prim_bytes;
     for (int off = 16; off > 0; off >>= 1) {
       p += __shfl_xor_sync(0xffffffffu, p, off);
       q += __shfl_xor_sync(0xffffffffu, q, off);
+      r += __shfl_xor_sync(0xffffffffu, r, off);
     }
     if (lane == 0) {
       atomicAdd(&ctl->pairs, (unsigned long long)p);
       atomicAdd(&ctl->prims, (unsigned long long)q);
+      atomicAdd(&ctl->prim_bytes, (unsigned long long)r);
     }
   }
 }
@@ -529,6 +532,7 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
     stats->paths = wh->pinned_ctl->paths;
     stats->node_visits = wh->pinned_ctl->pairs;
     stats->prim_tests = wh->pinned_ctl->prims;
+    stats->prim_bytes = wh->pinned_ctl->prim_bytes;
     stats->iterations = iterations;
     stats->launches = launches;
     stats->pool_size = pool;

@@ -37,6 +37,7 @@ __device__ __forceinline__ bool slab(float4 lo, float4 hi, v3 o, v3 inv, float t
 struct TraverseCounters {
   uint32_t pairs = 0;
   uint32_t prims = 0;
+  uint32_t prim_bytes = 0;
 };
 
 template <bool COUNT>
@@ -81,7 +82,10 @@ __device__ __forceinline__ void traverse_closest(const SceneDev& sc, v3 o, v3 d,
         if (inst != 0) ray_to_instance(sc, inst, oi, di);
         cur_inst = inst;
       }
-      if (COUNT) cnt.prims++;
+      if (COUNT) {
+        cnt.prims++;
+        cnt.prim_bytes += (type == PT_SPHERE) ? 16u : ((type >= PT_RECT_YZ && type <= PT_RECT_XY) ? 32u : 48u);
+      }
       float t;
       if (prim_t(type, sc.geom + 3 * (size_t)slot, oi, di, time, t_min, best_t, t)) {
         if (best_slot < 0 || t < best_t) {
