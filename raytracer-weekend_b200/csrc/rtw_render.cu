@@ -155,11 +155,26 @@ __global__ void k_wave_init(SceneDev sc, FrameDev f, WaveDev w) {
 }
 
 // ---- traversal -----------------------------------------------------------------------------------
+struct WaveIO {
+  const WaveDev& w;
+  const uint32_t* __restrict__ queue;
+  uint32_t slot;
+  __device__ __forceinline__ bool load(uint32_t i, v3& o, v3& d, float& time, float& t_min, float& t_max) {
+    slot = queue[i];
+    const float4 o4 = w.ray_o[slot], d4 = w.ray_d[slot];
+    o = mk(o4.x, o4.y, o4.z); d = mk(d4.x, d4.y, d4.z); time = o4.w;
+    t_min = 0.001f; t_max = __int_as_float(0x7f800000);  // lib.rs:102: world.hit(r, 0.001, f32::INFINITY)
+    return true;
+  }
+  __device__ __forceinline__ void store(uint32_t, v3, v3, float, int32_t hslot, float t, uint32_t) {
+    w.hit[slot] = make_int2(hslot, __float_as_int(t));
+  }
+};
+
 template <bool COUNT>
 __global__ void __launch_bounds__(128) k_wave_traverse(SceneDev sc, WaveDev w, uint32_t parity) {
   WaveCtl* ctl = w.ctl;
   const uint32_t count = ctl->count[parity];
-  const uint32_t* __restrict__ queue = w.queue[parity];
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     ctl->cursor_shade = 0;        // consumed by the shade kernel that follows
     ctl->count[parity ^ 1] = 0;   // the queue that shade kernel fills (its old content was consumed last iteration)
@@ -167,24 +182,8 @@ __global__ void __launch_bounds__(128) k_wave_traverse(SceneDev sc, WaveDev w, u
   }
   const uint32_t lane = threadIdx.x & 31;
   TraverseCounters cnt;
-  for (;;) {
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(&ctl->cursor_traverse, 32u);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= count) break;
-    uint32_t i = base + lane;
-    if (i < count) {
-      uint32_t slot = queue[i];
-      float4 o4 = w.ray_o[slot], d4 = w.ray_d[slot];
-      int32_t hslot;
-      float t;
-      uint32_t meta;
-      // lib.rs:102: world.hit(r, 0.001, f32::INFINITY)
-      traverse_closest<COUNT>(sc, mk(o4.x, o4.y, o4.z), mk(d4.x, d4.y, d4.z), o4.w, 0.001f, __int_as_float(0x7f800000),
-                              hslot, t, meta, cnt);
-      w.hit[slot] = make_int2(hslot, __float_as_int(t));
-    }
-  }
+  WaveIO io{w, w.queue[parity], 0};
+  traverse_persistent<COUNT>(sc, io, count, &ctl->cursor_traverse, cnt);
   if (COUNT) {
     uint32_t p = cnt.pairs, q = cnt.prims, r = cnt.prim_bytes;
     for (int off = 16; off > 0; off >>= 1) {

@@ -1,5 +1,7 @@
 // rtw_trace_closest: closest hit of a ray batch — the parity entry point.
 // One thread per ray; AoS rtw_ray in, AoS rtw_hit out (the full HitRecord of hittable/mod.rs:22-29).
+#include <algorithm>
+
 #include "rtw_scene.cuh"
 #include "rtw_traverse.cuh"
 
@@ -7,32 +9,13 @@ namespace rtw {
 
 namespace {
 
-template <int MODE>
-__global__ void __launch_bounds__(128) k_trace_batch(SceneDev sc, const rtw_ray* __restrict__ rays, uint64_t n,
-                                                     rtw_hit* __restrict__ hits) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float* rp = reinterpret_cast<const float*>(rays + i);
-  v3 o = mk(rp[0], rp[1], rp[2]), d = mk(rp[3], rp[4], rp[5]);
-  float time = rp[6], t_min = rp[7], t_max = rp[8];
+__device__ __forceinline__ void write_hit(const SceneDev& sc, rtw_hit* __restrict__ hits, uint64_t i, v3 o, v3 d, float time,
+                                          int32_t id, const float4* g, float best_t, uint32_t meta) {
   rtw_hit out;
   out.prim_id = -1; out.material_id = -1; out.t = 0.f;
   out.p[0] = out.p[1] = out.p[2] = 0.f;
   out.normal[0] = out.normal[1] = out.normal[2] = 0.f;
   out.u = out.v = 0.f; out.front_face = 0;
-  float best_t;
-  uint32_t meta;
-  int32_t id = -1;
-  const float4* g = nullptr;
-  if (MODE == RTW_TRACE_BVH) {
-    int32_t slot;
-    TraverseCounters cnt;
-    traverse_closest<false>(sc, o, d, time, t_min, t_max, slot, best_t, meta, cnt);
-    if (slot >= 0) { id = sc.slot_prim[slot]; g = sc.geom + 3 * (size_t)slot; }
-  } else {
-    brute_closest(sc, o, d, time, t_min, t_max, id, best_t, meta);
-    if (id >= 0) g = sc.raw_geom + 3 * (size_t)id;
-  }
   if (id >= 0) {
     HitRec rec;
     finalize_hit(sc, meta & 7u, meta >> RTW_META_TYPE_BITS, g, sc.prim_shade[id], o, d, time, best_t, true, rec);
@@ -47,19 +30,73 @@ __global__ void __launch_bounds__(128) k_trace_batch(SceneDev sc, const rtw_ray*
   hits[i] = out;
 }
 
+struct BatchIO {
+  const SceneDev& sc;
+  const rtw_ray* __restrict__ rays;
+  rtw_hit* __restrict__ hits;
+  __device__ __forceinline__ bool load(uint32_t i, v3& o, v3& d, float& time, float& t_min, float& t_max) {
+    const float* rp = reinterpret_cast<const float*>(rays + i);
+    o = mk(rp[0], rp[1], rp[2]); d = mk(rp[3], rp[4], rp[5]);
+    time = rp[6]; t_min = rp[7]; t_max = rp[8];
+    return true;
+  }
+  __device__ __forceinline__ void store(uint32_t i, v3 o, v3 d, float time, int32_t slot, float t, uint32_t meta) {
+    int32_t id = slot >= 0 ? sc.slot_prim[slot] : -1;
+    write_hit(sc, hits, i, o, d, time, id, sc.geom + 3 * (size_t)(slot >= 0 ? slot : 0), t, meta);
+  }
+};
+
+// the product path: the same persistent traversal the wavefront renderer runs
+__global__ void __launch_bounds__(128) k_trace_bvh(SceneDev sc, const rtw_ray* __restrict__ rays, uint32_t n,
+                                                   rtw_hit* __restrict__ hits, uint32_t* cursor) {
+  BatchIO io{sc, rays, hits};
+  TraverseCounters cnt;
+  traverse_persistent<false>(sc, io, n, cursor, cnt);
+}
+
+__global__ void __launch_bounds__(128) k_trace_brute(SceneDev sc, const rtw_ray* __restrict__ rays, uint64_t n,
+                                                     rtw_hit* __restrict__ hits) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* rp = reinterpret_cast<const float*>(rays + i);
+  v3 o = mk(rp[0], rp[1], rp[2]), d = mk(rp[3], rp[4], rp[5]);
+  float time = rp[6], t_min = rp[7], t_max = rp[8];
+  float best_t;
+  uint32_t meta;
+  int32_t id;
+  brute_closest(sc, o, d, time, t_min, t_max, id, best_t, meta);
+  write_hit(sc, hits, i, o, d, time, id, sc.raw_geom + 3 * (size_t)(id >= 0 ? id : 0), best_t, meta);
+}
+
 }  // namespace
 
 int trace_closest_device(rtw_scene* s, const rtw_ray* d_rays, uint64_t n, rtw_hit* d_hits, int mode, cudaStream_t st) {
   if (n == 0) return RTW_OK;
   const uint32_t T = 128;
-  uint64_t blocks = (n + T - 1) / T;
-  if (blocks > 0x7FFFFFFFull) return set_error(RTW_ERR_INVALID, "trace: batch too large");
-  if (mode == RTW_TRACE_BVH)
-    k_trace_batch<RTW_TRACE_BVH><<<(uint32_t)blocks, T, 0, st>>>(s->dev, d_rays, n, d_hits);
-  else if (mode == RTW_TRACE_BRUTE)
-    k_trace_batch<RTW_TRACE_BRUTE><<<(uint32_t)blocks, T, 0, st>>>(s->dev, d_rays, n, d_hits);
-  else
+  if (mode == RTW_TRACE_BVH) {
+    // persistent grid; batches above 2^31 rays are split
+    static thread_local int blocks_per_sm = 0;
+    if (!blocks_per_sm) {
+      RTW_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_trace_bvh, (int)T, 0));
+      blocks_per_sm = blocks_per_sm > 0 ? blocks_per_sm : 1;
+    }
+    uint32_t* cursor = nullptr;
+    RTW_CUDA_TRY(cudaMallocAsync((void**)&cursor, sizeof(uint32_t), st));
+    for (uint64_t done = 0; done < n;) {
+      uint32_t chunk = (uint32_t)std::min<uint64_t>(n - done, 1ull << 30);
+      RTW_CUDA_TRY(cudaMemsetAsync(cursor, 0, sizeof(uint32_t), st));
+      uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)blocks_per_sm * s->num_sms, (chunk + T - 1) / T);
+      k_trace_bvh<<<grid, T, 0, st>>>(s->dev, d_rays + done, chunk, d_hits + done, cursor);
+      done += chunk;
+    }
+    RTW_CUDA_TRY(cudaFreeAsync(cursor, st));
+  } else if (mode == RTW_TRACE_BRUTE) {
+    uint64_t blocks = (n + T - 1) / T;
+    if (blocks > 0x7FFFFFFFull) return set_error(RTW_ERR_INVALID, "trace: batch too large");
+    k_trace_brute<<<(uint32_t)blocks, T, 0, st>>>(s->dev, d_rays, n, d_hits);
+  } else {
     return set_error(RTW_ERR_INVALID, "trace: unknown mode");
+  }
   RTW_CUDA_TRY(cudaGetLastError());
   return RTW_OK;
 }

@@ -5,10 +5,24 @@
 // Result contract (exceptions 1-2): the primitive with the smallest accepted t;
 // among primitives with bit-equal t the one with the HIGHEST canonical id — exactly what the
 // reference's flat list in canonical order returns ("last tested wins", t == t_max is accepted).
+// The result is therefore independent of the traversal order, which leaves the scheduling free:
+//
+// traverse_persistent(): persistent threads in the style of Aila & Laine 2009 ("while-while" with
+// per-lane refill).  Every lane owns one ray.  Each trip of the outer loop (a) refills idle lanes
+// with new rays from a device-side cursor once enough of the warp is idle, (b) lets every lane walk
+// internal pairs until it holds a leaf, (c) tests the held leaves together.  Lanes that finish
+// write their hit and go idle until the next refill, so a warp never waits for its slowest ray
+// with more than REFILL_IDLE lanes parked.  (r01 baseline, one lane per ray and one if/else loop:
+// 7.45 of 32 threads active per issued instruction — profiles/r01a_ncu_full_baseline.csv.)
 #pragma once
 #include "rtw_device.cuh"
 
 namespace rtw {
+
+#define RTW_LINK_DONE ((int32_t)0x80000000)  // ~slot never reaches it (slot < 2^28)
+#ifndef RTW_REFILL_IDLE
+#define RTW_REFILL_IDLE 8  // refill once this many lanes of the warp are idle
+#endif
 
 // Slab test of one child record against the ray: aabb.rs:23-48 with (a) the reciprocal hoisted out
 // of the node loop (1/d is the same value every time), (b) a NON-strict reject (the reference
@@ -40,41 +54,80 @@ struct TraverseCounters {
   uint32_t prim_bytes = 0;
 };
 
-template <bool COUNT>
-__device__ __forceinline__ void traverse_closest(const SceneDev& sc, v3 o, v3 d, float time, float t_min, float t_max,
-                                                 int32_t& best_slot, float& best_t, uint32_t& best_meta,
-                                                 TraverseCounters& cnt) {
-  best_slot = -1;
-  best_t = t_max;
-  best_meta = 0;
-  int32_t best_id = -2;  // canonical id of best_slot, fetched lazily (only ties need it)
-  const v3 inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);  // aabb.rs:29
+// IO policy of traverse_persistent:
+//   bool load(uint32_t index, v3& o, v3& d, float& time, float& t_min, float& t_max)   fetch ray `index`
+//   void store(uint32_t index, v3 o, v3 d, float time, int32_t slot, float t, uint32_t meta)   publish its closest hit
+template <bool COUNT, class IO>
+__device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, uint32_t count, uint32_t* cursor,
+                                                    TraverseCounters& cnt) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t lane_lt = (1u << lane) - 1u;
+  bool active = false;
+  bool exhausted = false;  // warp-uniform: the cursor ran past `count`
+  // per-ray state
+  uint32_t index = 0;
+  v3 o = mk(0, 0, 0), d = mk(0, 0, 0), inv = mk(0, 0, 0), oi = o, di = d;
+  float time = 0.f, t_min = 0.f, best_t = 0.f;
+  int32_t best_slot = -1, best_id = -2, link = RTW_LINK_DONE;
+  uint32_t best_meta = 0, meta = 0, cur_inst = 0;
   int2 stack[RTW_STACK_SIZE];
   int sp = 0;
-  v3 oi = o, di = d;
-  uint32_t cur_inst = 0;
-  int32_t link = 0;
-  uint32_t meta = 0;
+
   for (;;) {
-    if (link >= 0) {
-      const float4* __restrict__ n = sc.nodes + 4 * (size_t)link;
-      float4 l0 = __ldg(n), l1 = __ldg(n + 1), r0 = __ldg(n + 2), r1 = __ldg(n + 3);
-      if (COUNT) cnt.pairs++;
-      float tl, tr;
-      bool hl = slab(l0, l1, o, inv, t_min, best_t, tl);
-      bool hr = slab(r0, r1, o, inv, t_min, best_t, tr);
-      if (hl && hr) {
-        bool left_first = tl <= tr;
-        int2 far_e = left_first ? make_int2(__float_as_int(r0.w), __float_as_int(r1.w))
-                                : make_int2(__float_as_int(l0.w), __float_as_int(l1.w));
-        stack[sp++] = far_e;
-        link = left_first ? __float_as_int(l0.w) : __float_as_int(r0.w);
-        meta = left_first ? __float_as_uint(l1.w) : __float_as_uint(r1.w);
-        continue;
+    // ---- (a) refill idle lanes -----------------------------------------------------------------
+    const uint32_t idle = __ballot_sync(0xffffffffu, !active);
+    if (idle != 0 && !exhausted && (__popc(idle) >= RTW_REFILL_IDLE || idle == 0xffffffffu)) {
+      const int leader = __ffs(idle) - 1;
+      uint32_t base = 0;
+      if ((int)lane == leader) base = atomicAdd(cursor, (uint32_t)__popc(idle));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (base + __popc(idle) >= count) exhausted = true;
+      if (!active) {
+        index = base + __popc(idle & lane_lt);
+        float t_max;
+        if (index < count && io.load(index, o, d, time, t_min, t_max)) {
+          inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);  // aabb.rs:29
+          best_t = t_max; best_slot = -1; best_id = -2; best_meta = 0;
+          oi = o; di = d; cur_inst = 0;
+          sp = 0; link = 0; meta = 0;
+          active = true;
+        }
       }
-      if (hl) { link = __float_as_int(l0.w); meta = __float_as_uint(l1.w); continue; }
-      if (hr) { link = __float_as_int(r0.w); meta = __float_as_uint(r1.w); continue; }
-    } else {
+    }
+    if (__ballot_sync(0xffffffffu, active) == 0) {
+      if (exhausted) break;
+      continue;
+    }
+    // ---- (b) walk internal pairs until this lane holds a leaf (or runs dry) --------------------------
+    if (active) {
+      while (link >= 0) {
+        const float4* __restrict__ n = sc.nodes + 4 * (size_t)link;
+        const float4 l0 = __ldg(n), l1 = __ldg(n + 1), r0 = __ldg(n + 2), r1 = __ldg(n + 3);
+        if (COUNT) cnt.pairs++;
+        float tl, tr;
+        const bool hl = slab(l0, l1, o, inv, t_min, best_t, tl);
+        const bool hr = slab(r0, r1, o, inv, t_min, best_t, tr);
+        if (hl && hr) {
+          const bool left_first = tl <= tr;
+          stack[sp++] = left_first ? make_int2(__float_as_int(r0.w), __float_as_int(r1.w))
+                                   : make_int2(__float_as_int(l0.w), __float_as_int(l1.w));
+          link = left_first ? __float_as_int(l0.w) : __float_as_int(r0.w);
+          meta = left_first ? __float_as_uint(l1.w) : __float_as_uint(r1.w);
+        } else if (hl) {
+          link = __float_as_int(l0.w); meta = __float_as_uint(l1.w);
+        } else if (hr) {
+          link = __float_as_int(r0.w); meta = __float_as_uint(r1.w);
+        } else if (sp > 0) {
+          const int2 e = stack[--sp];
+          link = e.x; meta = (uint32_t)e.y;
+        } else {
+          link = RTW_LINK_DONE;
+        }
+      }
+    }
+    __syncwarp();
+    // ---- (c) test the held leaf -------------------------------------------------------------------------
+    if (active && link != RTW_LINK_DONE) {
       const uint32_t slot = (uint32_t)(~link);
       const uint32_t type = meta & 7u, inst = meta >> RTW_META_TYPE_BITS;
       if (inst != cur_inst) {
@@ -92,15 +145,21 @@ __device__ __forceinline__ void traverse_closest(const SceneDev& sc, v3 o, v3 d,
           best_t = t; best_slot = (int32_t)slot; best_meta = meta; best_id = -2;
         } else {  // t == best_t: the later primitive of the canonical order wins (hittable/mod.rs:61-66)
           if (best_id == -2) best_id = __ldg(sc.slot_prim + best_slot);
-          int32_t id = __ldg(sc.slot_prim + slot);
+          const int32_t id = __ldg(sc.slot_prim + slot);
           if (id > best_id) { best_slot = (int32_t)slot; best_meta = meta; best_id = id; }
         }
       }
+      if (sp > 0) {
+        const int2 e = stack[--sp];
+        link = e.x; meta = (uint32_t)e.y;
+      } else {
+        link = RTW_LINK_DONE;
+      }
     }
-    if (sp == 0) break;
-    int2 e = stack[--sp];
-    link = e.x;
-    meta = (uint32_t)e.y;
+    if (active && link == RTW_LINK_DONE) {
+      io.store(index, o, d, time, best_slot, best_t, best_meta);
+      active = false;
+    }
   }
 }
 
