@@ -103,8 +103,8 @@ typedef struct rtw_render_stats {
   uint64_t paths;         /* camera paths started                                          */
   uint64_t node_visits;   /* 64-byte child-pair fetches (only with COUNT_TRAVERSAL)        */
   uint64_t prim_tests;    /* primitive intersection tests (only with COUNT_TRAVERSAL)      */
-  uint64_t prim_bytes;    /* geometry bytes those tests fetched: sphere 16, rect 32,       */
-                          /*   moving sphere / triangle 48 (only with COUNT_TRAVERSAL)     */
+  uint64_t prim_bytes;    /* bytes those tests fetched: 4 (slot meta) + geometry: sphere   */
+                          /*   16, rect 32, moving sphere / triangle 48 (COUNT_TRAVERSAL)  */
   uint32_t iterations;    /* wavefront iterations (one traverse + one shade launch each)   */
   uint32_t launches;      /* kernels launched by this call                                 */
   uint32_t pool_size;     /* slots actually used                                           */
@@ -127,8 +127,8 @@ typedef struct rtw_build_stats {
 
 /* 32-byte BVH child record as it lies in HBM; two of them (left, right) form the 64-byte
  * "pair" that one traversal step fetches with 4 LDG.128.  link >= 0: index of the child's own
- * pair; link < 0: leaf, primitive slot = ~link.  meta (leaves): bits 0-2 primitive type,
- * bits 3-31 instance (transform chain) index. */
+ * pair; link < 0: leaf = the contiguous primitive-slot range [~link, ~link + meta)
+ * (meta = primitive count; the SAH collapse of the build decides how many). */
 typedef struct rtw_bvh_node {
   float bmin[3];
   int32_t link;

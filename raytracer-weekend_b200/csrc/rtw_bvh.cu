@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "rtw_scene.cuh"
@@ -301,9 +302,9 @@ __device__ __forceinline__ int delta(const uint64_t* __restrict__ keys, int n, i
   return __clzll((long long)(a ^ b));
 }
 
-// parent encoding: (pair index << 1) | side
+// parent encoding: (pair index << 1) | side.  node_range[i] = (first slot, slot count) of the subtree.
 __global__ void k_karras(int n, const uint64_t* __restrict__ keys, uint32_t* __restrict__ node_parent,
-                         uint32_t* __restrict__ leaf_parent) {
+                         uint32_t* __restrict__ leaf_parent, uint2* __restrict__ node_range) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1) return;
   int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
@@ -327,15 +328,18 @@ __global__ void k_karras(int n, const uint64_t* __restrict__ keys, uint32_t* __r
   if (lo == gamma) leaf_parent[gamma] = me | 0u; else node_parent[gamma] = me | 0u;
   if (hi == gamma + 1) leaf_parent[gamma + 1] = me | 1u; else node_parent[gamma + 1] = me | 1u;
   if (i == 0) node_parent[0] = 0xFFFFFFFFu;
+  node_range[i] = make_uint2((uint32_t)lo, (uint32_t)(hi - lo + 1));
 }
 
-// Kernel: leaves.  Slot s holds primitive vals[s]; copies its geometry into slot order.
+// Kernel: leaves.  Slot s holds primitive vals[s]; copies its geometry and meta into slot order.
 __global__ void k_emit_leaves(uint32_t n, const uint32_t* __restrict__ vals, const float4* __restrict__ enc,
-                              float4* __restrict__ geom, int32_t* __restrict__ slot_prim) {
+                              const uint32_t* __restrict__ meta, float4* __restrict__ geom, int32_t* __restrict__ slot_prim,
+                              uint32_t* __restrict__ slot_meta) {
   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
   uint32_t id = vals[s];
   slot_prim[s] = (int32_t)id;
+  slot_meta[s] = meta[id];
   geom[3 * (size_t)s] = enc[3 * (size_t)id];
   geom[3 * (size_t)s + 1] = enc[3 * (size_t)id + 1];
   geom[3 * (size_t)s + 2] = enc[3 * (size_t)id + 2];
@@ -346,29 +350,47 @@ __device__ __forceinline__ void store_record(float4* nodes, uint32_t rec, v3 lo,
   __stcg(&nodes[2 * (size_t)rec + 1], make_float4(hi.x, hi.y, hi.z, __uint_as_float(meta)));
 }
 
-// Kernel: bottom-up refit.  One thread per leaf; the second thread to reach a pair owns it.
-// out_root: 6 floats root box + height (as uint bits in out_root_height).
-__global__ void k_refit(uint32_t n, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ meta,
-                        const float4* __restrict__ box_lo, const float4* __restrict__ box_hi, float pad,
-                        const uint32_t* __restrict__ node_parent, const uint32_t* __restrict__ leaf_parent,
-                        uint32_t* __restrict__ flags, uint32_t* __restrict__ heights, float4* __restrict__ nodes,
-                        float* __restrict__ out_root, uint32_t* __restrict__ out_height) {
+__device__ __forceinline__ float half_area(v3 lo, v3 hi) {
+  float dx = fmaxf(hi.x - lo.x, 0.f), dy = fmaxf(hi.y - lo.y, 0.f), dz = fmaxf(hi.z - lo.z, 0.f);
+  return dx * dy + dy * dz + dz * dx;
+}
+
+// Kernel: bottom-up refit + SAH leaf collapse.  One thread per Karras leaf; the second thread to
+// reach a pair owns it (atomic flag), unions the child boxes (Aabb::surrounding_box, aabb.rs:74-88)
+// and decides whether the subtree stays a hierarchy or becomes ONE leaf over its contiguous slot
+// range:  C_leaf = n * C_PRIM   vs   C_split = C_PAIR + (SA(l) C(l) + SA(r) C(r)) / SA(node).
+// Leaves are ranges: link = ~first_slot, meta = primitive count.  Scenes whose boxes all overlap
+// (a Cornell box: every wall spans the room) collapse into a single converged primitive loop.
+struct RefitParams {
+  float pad;        // box padding (see file header)
+  float c_pair;     // cost of fetching + testing one child pair
+  float c_prim;     // cost of one primitive test
+  uint32_t max_leaf;
+  uint32_t force_flat;  // collapse the root unconditionally (tiny scene)
+};
+
+__global__ void k_refit(uint32_t n, const uint32_t* __restrict__ vals, const float4* __restrict__ box_lo,
+                        const float4* __restrict__ box_hi, RefitParams rp, const uint32_t* __restrict__ node_parent,
+                        const uint32_t* __restrict__ leaf_parent, const uint2* __restrict__ node_range,
+                        uint32_t* __restrict__ flags, uint32_t* __restrict__ heights, float* __restrict__ node_cost,
+                        uint32_t* __restrict__ collapsed, float4* __restrict__ nodes, float* __restrict__ out_root,
+                        uint32_t* __restrict__ out_info) {
   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
   uint32_t id = vals[s];
   float4 l4 = box_lo[id], h4 = box_hi[id];
-  v3 lo = mk(l4.x - pad, l4.y - pad, l4.z - pad), hi = mk(h4.x + pad, h4.y + pad, h4.z + pad);
+  v3 lo = mk(l4.x - rp.pad, l4.y - rp.pad, l4.z - rp.pad), hi = mk(h4.x + rp.pad, h4.y + rp.pad, h4.z + rp.pad);
   const float INF = __int_as_float(0x7f800000);
   if (n == 1) {
-    store_record(nodes, 0, lo, hi, ~0, meta[id]);
-    store_record(nodes, 1, mk(INF, INF, INF), mk(-INF, -INF, -INF), ~0, meta[id]);
+    store_record(nodes, 0, lo, hi, ~0, 1u);
+    store_record(nodes, 1, mk(INF, INF, INF), mk(-INF, -INF, -INF), ~0, 0u);
     out_root[0] = lo.x; out_root[1] = lo.y; out_root[2] = lo.z;
     out_root[3] = hi.x; out_root[4] = hi.y; out_root[5] = hi.z;
-    *out_height = 1;
+    out_info[0] = 1; out_info[1] = 1;
     return;
   }
   uint32_t par = leaf_parent[s];
-  store_record(nodes, par, lo, hi, ~(int32_t)s, meta[id]);
+  store_record(nodes, par, lo, hi, ~(int32_t)s, 1u);
   uint32_t h = 1;  // height of the subtree rooted at the parent pair, counted in pairs
   for (;;) {
     uint32_t p = par >> 1;
@@ -378,19 +400,59 @@ __global__ void k_refit(uint32_t n, const uint32_t* __restrict__ vals, const uin
     __threadfence();
     float4 a0 = __ldcg(&nodes[4 * (size_t)p]), a1 = __ldcg(&nodes[4 * (size_t)p + 1]);
     float4 b0 = __ldcg(&nodes[4 * (size_t)p + 2]), b1 = __ldcg(&nodes[4 * (size_t)p + 3]);
-    // Aabb::surrounding_box (aabb.rs:74-88)
     v3 ulo = mk(fminf(a0.x, b0.x), fminf(a0.y, b0.y), fminf(a0.z, b0.z));
     v3 uhi = mk(fmaxf(a1.x, b1.x), fmaxf(a1.y, b1.y), fmaxf(a1.z, b1.z));
+    // SAH: cost of the children as they stand now (leaf range or hierarchy)
+    int32_t la = __float_as_int(a0.w), lb = __float_as_int(b0.w);
+    float ca = la < 0 ? (float)__float_as_uint(a1.w) * rp.c_prim : __ldcg(&node_cost[la]);
+    float cb = lb < 0 ? (float)__float_as_uint(b1.w) * rp.c_prim : __ldcg(&node_cost[lb]);
+    float sa = half_area(ulo, uhi);
+    float c_split = rp.c_pair + (sa > 0.f ? (half_area(mk(a0.x, a0.y, a0.z), mk(a1.x, a1.y, a1.z)) * ca +
+                                              half_area(mk(b0.x, b0.y, b0.z), mk(b1.x, b1.y, b1.z)) * cb) / sa
+                                           : ca + cb);
+    uint2 rg = node_range[p];
+    float c_leaf = (float)rg.y * rp.c_prim;
+    bool collapse = rg.y <= rp.max_leaf && !(c_leaf > c_split);
+    if (p == 0 && rp.force_flat) collapse = true;
+    node_cost[p] = collapse ? c_leaf : c_split;
+    collapsed[p] = collapse ? 1u : 0u;
     h = atomicMax(&heights[p], 0u);
     if (p == 0) {
+      if (collapse) {  // the whole scene is one leaf: pair 0 = {that leaf, empty}
+        store_record(nodes, 0, ulo, uhi, ~(int32_t)rg.x, rg.y);
+        store_record(nodes, 1, mk(INF, INF, INF), mk(-INF, -INF, -INF), ~0, 0u);
+      }
       out_root[0] = ulo.x; out_root[1] = ulo.y; out_root[2] = ulo.z;
       out_root[3] = uhi.x; out_root[4] = uhi.y; out_root[5] = uhi.z;
-      *out_height = h;
+      out_info[0] = h; out_info[1] = collapse ? 1u : 0u;
       return;
     }
     par = node_parent[p];
-    store_record(nodes, par, ulo, uhi, (int32_t)p, 0u);
+    if (collapse) store_record(nodes, par, ulo, uhi, ~(int32_t)rg.x, rg.y);
+    else store_record(nodes, par, ulo, uhi, (int32_t)p, 0u);
     h = h + 1;
+  }
+}
+
+// Kernel: inside every final multi-primitive leaf, order the primitives by (instance, type) — the
+// traversal re-transforms / re-permutes the ray only when that key changes.  A leaf is final when
+// its pair collapsed and its parent did not.  Stable insertion sort of <= max_leaf entries of `vals`.
+__global__ void k_sort_leaf_ranges(uint32_t n_internal, const uint32_t* __restrict__ collapsed,
+                                   const uint32_t* __restrict__ node_parent, const uint2* __restrict__ node_range,
+                                   const uint32_t* __restrict__ meta, uint32_t* __restrict__ vals) {
+  uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_internal || !collapsed[p]) return;
+  if (p != 0 && collapsed[node_parent[p] >> 1]) return;
+  uint2 rg = node_range[p];
+  for (uint32_t i = 1; i < rg.y; ++i) {
+    uint32_t v = vals[rg.x + i];
+    uint32_t key = meta[v];
+    uint32_t j = i;
+    while (j > 0 && meta[vals[rg.x + j - 1]] > key) {
+      vals[rg.x + j] = vals[rg.x + j - 1];
+      --j;
+    }
+    vals[rg.x + j] = v;
   }
 }
 
@@ -454,6 +516,8 @@ int build_scene_device(rtw_scene* s, float time0, float time1, rtw_build_stats* 
   // ---- persistent outputs ---------------------------------------------------------------------
   float4 *d_enc, *d_geom, *d_nodes;
   int32_t* d_slot_prim;
+  uint32_t* d_slot_meta;
+  if ((rc = dev_alloc(s, &d_slot_meta, n))) return rc;
   if ((rc = dev_alloc(s, &d_enc, 3 * (size_t)n))) return rc;
   if ((rc = dev_alloc(s, &d_geom, 3 * (size_t)n))) return rc;
   if ((rc = dev_alloc(s, &d_nodes, 4 * (size_t)d.num_nodes))) return rc;
@@ -473,8 +537,12 @@ int build_scene_device(rtw_scene* s, float time0, float time1, rtw_build_stats* 
   if ((rc = salloc((void**)&d_raw, sizeof(float4) * 3 * (size_t)n))) return rc;
   RTW_CUDA_TRY(cudaMemcpy(d_raw, s->raw_geom.data(), sizeof(float4) * 3 * (size_t)n, cudaMemcpyHostToDevice));
   uint64_t *d_k0, *d_k1;
-  uint32_t *d_v0, *d_v1, *d_hist, *d_bounds, *d_nparent, *d_lparent, *d_flags, *d_heights, *d_height;
-  float* d_root;
+  uint32_t *d_v0, *d_v1, *d_hist, *d_bounds, *d_nparent, *d_lparent, *d_flags, *d_heights, *d_info, *d_collapsed;
+  if ((rc = salloc((void**)&d_collapsed, 4ull * n))) return rc;
+  uint2* d_nrange;
+  float *d_root, *d_ncost;
+  if ((rc = salloc((void**)&d_nrange, 8ull * n))) return rc;
+  if ((rc = salloc((void**)&d_ncost, 4ull * n))) return rc;
   if ((rc = salloc((void**)&d_lo, sizeof(float4) * n))) return rc;
   if ((rc = salloc((void**)&d_hi, sizeof(float4) * n))) return rc;
   if ((rc = salloc((void**)&d_k0, 8ull * n))) return rc;
@@ -488,7 +556,7 @@ int build_scene_device(rtw_scene* s, float time0, float time1, rtw_build_stats* 
   if ((rc = salloc((void**)&d_flags, 4ull * n))) return rc;
   if ((rc = salloc((void**)&d_heights, 4ull * n))) return rc;
   if ((rc = salloc((void**)&d_root, 4 * 8))) return rc;
-  d_height = (uint32_t*)(d_root + 6);
+  d_info = (uint32_t*)(d_root + 6);
 
   const uint32_t T = 256, G = (n + T - 1) / T;
   k_prim_setup<<<G, T>>>(n, d_raw, d.prim_meta, d.inst_range, d.inst_ops, time0, time1, d_enc, d_lo, d_hi);
@@ -506,16 +574,30 @@ int build_scene_device(rtw_scene* s, float time0, float time1, rtw_build_stats* 
     std::swap(d_k0, d_k1);
     std::swap(d_v0, d_v1);
   }
-  k_emit_leaves<<<G, T>>>(n, d_v0, d_enc, d_geom, d_slot_prim);
   RTW_CUDA_TRY(cudaMemset(d_flags, 0, 4ull * n));
   RTW_CUDA_TRY(cudaMemset(d_heights, 0, 4ull * n));
-  if (n > 1) k_karras<<<G, T>>>((int)n, d_k0, d_nparent, d_lparent);
+  if (n > 1) k_karras<<<G, T>>>((int)n, d_k0, d_nparent, d_lparent, d_nrange);
   uint32_t h_bounds[8];
   RTW_CUDA_TRY(cudaMemcpy(h_bounds, d_bounds, sizeof(h_bounds), cudaMemcpyDeviceToHost));
   const float amax = ord2f(h_bounds[6]);
-  const float pad = amax * (1.0f / 1048576.0f);
-  k_refit<<<G, T>>>(n, d_v0, d.prim_meta, d_lo, d_hi, pad, d_nparent, d_lparent, d_flags, d_heights, d_nodes, d_root,
-                    d_height);
+  RefitParams rp;
+  rp.pad = amax * (1.0f / 1048576.0f);
+  // SAH constants (measured on B200, profiles/r01_sah_sweep.txt): pair step = primitive test = 1 is
+  // best for the mesh scenes; a scene of <= 32 primitives is kept FLAT (one leaf): every lane of a
+  // warp then walks the same primitive list in the same order — no hierarchy beats that on a SIMT
+  // machine (Cornell box: +11% over the best hierarchy).  Overridable for experiments.
+  rp.c_pair = 1.0f;
+  rp.c_prim = 1.0f;
+  rp.max_leaf = 32;
+  uint32_t flat_max = 32;
+  if (const char* e = getenv("RTW_SAH_PAIR_COST")) rp.c_pair = (float)atof(e);
+  if (const char* e = getenv("RTW_MAX_LEAF")) rp.max_leaf = (uint32_t)std::max(1, atoi(e));
+  if (const char* e = getenv("RTW_FLAT_SCENE_MAX")) flat_max = (uint32_t)std::max(0, atoi(e));
+  rp.force_flat = (n <= flat_max && n <= rp.max_leaf) ? 1u : 0u;
+  k_refit<<<G, T>>>(n, d_v0, d_lo, d_hi, rp, d_nparent, d_lparent, d_nrange, d_flags, d_heights, d_ncost, d_collapsed,
+                    d_nodes, d_root, d_info);
+  if (n > 1) k_sort_leaf_ranges<<<G, T>>>(n - 1, d_collapsed, d_nparent, d_nrange, d.prim_meta, d_v0);
+  k_emit_leaves<<<G, T>>>(n, d_v0, d_enc, d.prim_meta, d_geom, d_slot_prim, d_slot_meta);
   RTW_CUDA_TRY(cudaGetLastError());
   RTW_CUDA_TRY(cudaEventRecord(ev[2]));
   RTW_CUDA_TRY(cudaEventSynchronize(ev[2]));
@@ -529,6 +611,7 @@ int build_scene_device(rtw_scene* s, float time0, float time1, rtw_build_stats* 
   d.geom = d_geom;
   d.raw_geom = d_enc;
   d.slot_prim = d_slot_prim;
+  d.slot_meta = d_slot_meta;
 
   float ms_up = 0.f, ms_build = 0.f;
   cudaEventElapsedTime(&ms_up, ev[0], ev[1]);

@@ -69,7 +69,8 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
   v3 o = mk(0, 0, 0), d = mk(0, 0, 0), inv = mk(0, 0, 0), oi = o, di = d;
   float time = 0.f, t_min = 0.f, best_t = 0.f;
   int32_t best_slot = -1, best_id = -2, link = RTW_LINK_DONE;
-  uint32_t best_meta = 0, meta = 0, cur_inst = 0;
+  uint32_t best_meta = 0, meta = 0, cur_inst = 0, cur_pm = 0xffffffffu;
+  float oA = 0.f, oB = 0.f, oK = 0.f, dA = 0.f, dB = 0.f, dK = 0.f;  // ray permuted for the current rectangle run
   int2 stack[RTW_STACK_SIZE];
   int sp = 0;
 
@@ -88,7 +89,7 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
         if (index < count && io.load(index, o, d, time, t_min, t_max)) {
           inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);  // aabb.rs:29
           best_t = t_max; best_slot = -1; best_id = -2; best_meta = 0;
-          oi = o; di = d; cur_inst = 0;
+          oi = o; di = d; cur_inst = 0; cur_pm = 0xffffffffu;
           sp = 0; link = 0; meta = 0;
           active = true;
         }
@@ -126,27 +127,50 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
       }
     }
     __syncwarp();
-    // ---- (c) test the held leaf -------------------------------------------------------------------------
+    // ---- (c) test the primitives of the held leaf (a contiguous slot range) ---------------------------
+    // Inside a leaf the build sorted the slots by (instance, type): the ray is re-transformed /
+    // re-permuted only when that key changes (cur_pm caches it).
     if (active && link != RTW_LINK_DONE) {
-      const uint32_t slot = (uint32_t)(~link);
-      const uint32_t type = meta & 7u, inst = meta >> RTW_META_TYPE_BITS;
-      if (inst != cur_inst) {
-        oi = o; di = d;
-        if (inst != 0) ray_to_instance(sc, inst, oi, di);
-        cur_inst = inst;
-      }
-      if (COUNT) {
-        cnt.prims++;
-        cnt.prim_bytes += (type == PT_SPHERE) ? 16u : ((type >= PT_RECT_YZ && type <= PT_RECT_XY) ? 32u : 48u);
-      }
-      float t;
-      if (prim_t(type, sc.geom + 3 * (size_t)slot, oi, di, time, t_min, best_t, t)) {
-        if (best_slot < 0 || t < best_t) {
-          best_t = t; best_slot = (int32_t)slot; best_meta = meta; best_id = -2;
-        } else {  // t == best_t: the later primitive of the canonical order wins (hittable/mod.rs:61-66)
-          if (best_id == -2) best_id = __ldg(sc.slot_prim + best_slot);
-          const int32_t id = __ldg(sc.slot_prim + slot);
-          if (id > best_id) { best_slot = (int32_t)slot; best_meta = meta; best_id = id; }
+      const uint32_t first = (uint32_t)(~link);
+      const uint32_t nprim = meta;
+      for (uint32_t k = 0; k < nprim; ++k) {
+        const uint32_t slot = first + k;
+        const uint32_t pm = __ldg(sc.slot_meta + slot);
+        const uint32_t type = pm & 7u;
+        if (pm != cur_pm) {
+          const uint32_t inst = pm >> RTW_META_TYPE_BITS;
+          if (inst != cur_inst) {
+            oi = o; di = d;
+            if (inst != 0) ray_to_instance(sc, inst, oi, di);
+            cur_inst = inst;
+          }
+          if (type >= PT_RECT_YZ && type <= PT_RECT_XY) {
+            const int axis = (int)type - (int)PT_RECT_YZ;
+            const int A = (axis == 0) ? 1 : 0, B = (axis == 2) ? 1 : 2;
+            oA = comp(oi, A); oB = comp(oi, B); oK = comp(oi, axis);
+            dA = comp(di, A); dB = comp(di, B); dK = comp(di, axis);
+          }
+          cur_pm = pm;
+        }
+        if (COUNT) {
+          cnt.prims++;
+          cnt.prim_bytes += 4u + ((type == PT_SPHERE) ? 16u : ((type >= PT_RECT_YZ && type <= PT_RECT_XY) ? 32u : 48u));
+        }
+        const float4* __restrict__ g = sc.geom + 3 * (size_t)slot;
+        float t;
+        bool hit;
+        if (type >= PT_RECT_YZ && type <= PT_RECT_XY)
+          hit = rect_t_perm(oA, oB, oK, dA, dB, dK, t_min, best_t, __ldg(g), __ldg(reinterpret_cast<const float*>(g + 1)), t);
+        else
+          hit = prim_t(type, g, oi, di, time, t_min, best_t, t);
+        if (hit) {
+          if (best_slot < 0 || t < best_t) {
+            best_t = t; best_slot = (int32_t)slot; best_meta = pm; best_id = -2;
+          } else {  // t == best_t: the later primitive of the canonical order wins (hittable/mod.rs:61-66)
+            if (best_id == -2) best_id = __ldg(sc.slot_prim + best_slot);
+            const int32_t id = __ldg(sc.slot_prim + slot);
+            if (id > best_id) { best_slot = (int32_t)slot; best_meta = pm; best_id = id; }
+          }
         }
       }
       if (sp > 0) {
