@@ -346,7 +346,7 @@ std::vector<Pixel> Raytracer::render(rtw_sink* sink, uint64_t seed, rtw_render_s
 // ---------------------------------------------------------------------------------------------
 namespace {
 struct ImageAsset { std::vector<uint8_t> rgb; uint32_t w, h; };
-struct MeshAsset { std::vector<float> v, n, uv; };
+struct MeshAsset { std::vector<float> v, n, uv; bool uses_mtl = false; };
 std::map<std::string, ImageAsset>& image_registry() { static std::map<std::string, ImageAsset> r; return r; }
 std::map<std::string, MeshAsset>& mesh_registry() { static std::map<std::string, MeshAsset> r; return r; }
 std::string& asset_dir() { static std::string d = "assets"; return d; }
@@ -413,6 +413,7 @@ bool read_rtwm(const std::string& path, MeshAsset& out) {
   f.read((char*)hdr, 12);
   if (!f || memcmp(magic, "RTWM", 4) != 0 || hdr[0] != 1) throw Error("bad .rtwm file: " + path);
   size_t n = hdr[1];
+  out.uses_mtl = (hdr[2] & 4) != 0;
   out.v.resize(n * 9);
   f.read((char*)out.v.data(), (std::streamsize)(n * 9 * 4));
   if (hdr[2] & 1) { out.n.resize(n * 9); f.read((char*)out.n.data(), (std::streamsize)(n * 9 * 4)); }
@@ -427,7 +428,9 @@ void register_image(const std::string& path, std::vector<uint8_t> rgb, uint32_t 
   image_registry()[path] = ImageAsset{std::move(rgb), w, h};
 }
 void register_mesh(const std::string& path, std::vector<float> v, std::vector<float> n, std::vector<float> uv) {
-  mesh_registry()[path] = MeshAsset{std::move(v), std::move(n), std::move(uv)};
+  MeshAsset a;
+  a.v = std::move(v); a.n = std::move(n); a.uv = std::move(uv);
+  mesh_registry()[path] = std::move(a);
 }
 void set_asset_dir(const std::string& dir) { asset_dir() = dir; }
 
@@ -612,7 +615,13 @@ HittablePtr load_wavefront_obj(const std::string& path, MaterialPtr override_mat
     fill_defaults(d);
     tris.push_back(std::make_shared<TriangleMesh>(d.v, any_n ? d.n : std::vector<float>(), any_uv ? d.uv : std::vector<float>(), per_face));
   } else {
-    // binary fixture: carries no material names -> the reference's "no usemtl" default
+    // binary fixture: carries geometry only.  Without usemtl the reference gives every face the magenta
+    // emitter (triangular.rs:177-182); with usemtl it needs the MTL + its map_Kd image, which a fixture
+    // cannot provide (for the monument the PNG is missing from the reference tree itself).
+    MeshAsset probe;
+    if ((read_rtwm(asset_dir() + "/" + stem_of(path) + ".rtwm", probe) || read_rtwm(path, probe)) && probe.uses_mtl)
+      throw Error("load_wavefront_obj(\"" + path + "\"): the OBJ names materials (usemtl) but neither the OBJ/MTL files nor "
+                  "their map_Kd image are available: no decoded image for the material library");
     tris.push_back(load_mesh(path, std::make_shared<DiffuseLight>(SolidColor::new_rgb(1.0f, 0.0f, 1.0f))));
   }
   return std::make_shared<BvhNode>(tris, 0.0f, 1.0f);  // triangular.rs:259

@@ -1,0 +1,143 @@
+"""The C-ABI boundary: every entry point include/*.h declares is exported, struct layouts match the
+bindings, flattening is correct (host logic, no GPU needed) and — without a CUDA device — every
+compute call fails loudly instead of falling back to anything."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import raytracer_weekend_b200 as rtw
+from conftest import HAS_GPU, ROOT, ORACLE_LIB
+
+HDR = os.path.join(ROOT, "include", "rtw_cuda.h")
+SINK_HDR = os.path.join(ROOT, "include", "rtw_sink.h")
+
+
+def declared_functions(path, prefix):
+    txt = open(path).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(" + prefix + r"[a-z0-9_]+)\s*\(", txt)))
+
+
+def exported(lib):
+    out = subprocess.run(["nm", "-D", "--defined-only", lib], stdout=subprocess.PIPE, text=True, check=True).stdout
+    return {l.split()[-1] for l in out.splitlines() if " T " in l}
+
+
+def test_cuda_library_exports_every_declared_symbol():
+    names = declared_functions(HDR, "rtw_")
+    assert len(names) >= 35
+    missing = [n for n in names if n not in exported(rtw.CUDA_LIB)]
+    assert not missing, missing
+
+
+def test_host_library_exports_sink_api():
+    names = declared_functions(SINK_HDR, "rtwh_")
+    assert set(names) >= {"rtwh_sink_open", "rtwh_sink_close", "rtwh_last_error"}
+    assert not [n for n in names if n not in exported(rtw.HOST_LIB)]
+
+
+def test_oracle_mirrors_the_emit_and_render_abi():
+    # the oracle is driven through the same sink table: same names, prefix orc_
+    ex = exported(ORACLE_LIB)
+    for n in rtw.api._SINK_FUNCS:
+        assert "orc_" + n in ex, n
+    assert "orc_trace_closest" in ex
+
+
+def test_product_libraries_do_not_link_the_oracle():
+    for lib in (rtw.CUDA_LIB, rtw.HOST_LIB, os.path.join(rtw.PKG_DIR, "bin", "console_app")):
+        out = subprocess.run(["ldd", lib], stdout=subprocess.PIPE, text=True).stdout
+        assert "oracle" not in out
+        assert "orc_" not in subprocess.run(["nm", "-D", lib], stdout=subprocess.PIPE, text=True).stdout
+    # and no product source mentions the oracle directory
+    for base, _, files in os.walk(rtw.PKG_DIR):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp")):
+                txt = open(os.path.join(base, f), errors="replace").read()
+                assert "liboracle" not in txt and "oracle/" not in txt, os.path.join(base, f)
+
+
+def test_struct_layouts_match_the_header():
+    # sizes the C compiler sees (static_asserts compiled on the fly)
+    src = f'''#include "{HDR}"
+    #include <stdio.h>
+    int main() {{ printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(rtw_ray), sizeof(rtw_hit), sizeof(rtw_camera),
+      sizeof(rtw_render_params), sizeof(rtw_render_stats), sizeof(rtw_build_stats), sizeof(rtw_bvh_node)); return 0; }}'''
+    exe = "/tmp/rtw_sizes"
+    subprocess.run(["/usr/bin/gcc", "-x", "c", "-", "-o", exe], input=src, text=True, check=True)
+    sizes = [int(x) for x in subprocess.run([exe], stdout=subprocess.PIPE, text=True, check=True).stdout.split()]
+    assert sizes == [rtw.RAY_DTYPE.itemsize, rtw.HIT_DTYPE.itemsize, C.sizeof(rtw.Camera), C.sizeof(rtw.RenderParams),
+                     C.sizeof(rtw.RenderStats), C.sizeof(rtw.BuildStats), rtw.BVH_NODE_DTYPE.itemsize]
+
+
+def test_flatten_canonical_order_and_instances():
+    b = rtw.cuda_backend()
+    with b.new_scene() as s:
+        white = s.lambertian_rgb(.73, .73, .73)
+        light = s.diffuse_light_rgb(15, 15, 15)
+        assert s.yz_rect(0, 555, 0, 555, 555, white) == 0
+        assert s.xz_rect(213, 343, 227, 332, 554, light) == 1
+        s.push_translation((265, 0, 295))
+        s.push_rotation_y(15.0)
+        assert s.cuboid((0, 0, 0), (165, 330, 165), white) == 2
+        s.pop_transform()
+        s.pop_transform()
+        s.begin_group()
+        assert s.sphere((0, 0, 0), 1.0, white) == 8
+        assert s.triangles(np.arange(18, dtype=np.float32).reshape(2, 9), white) == 9
+        s.end_group()
+        assert s.num_prims == 11
+        # types: 2 yz, 3 xz, 4 xy, 0 sphere, 5 triangle ; cuboid order XY,XY,XZ,XZ,YZ,YZ (rectangular.rs:177-234)
+        assert [s.prim_info(i)[0] for i in range(11)] == [2, 3, 4, 4, 3, 3, 2, 2, 0, 5, 5]
+        assert [s.prim_info(i)[1] for i in range(11)] == [0, 0, 1, 1, 1, 1, 1, 1, 0, 0, 0]
+        assert [s.prim_info(i)[2] for i in range(11)] == [white, light] + [white] * 9
+        ops = s.instance_ops(1)
+        assert [k for k, _ in ops] == [0, 1]  # outermost first: Translation then YRotation
+        assert ops[0][1] == (265.0, 0.0, 295.0)
+        rad = np.float32(15.0) * np.float32(np.float32(np.pi) / np.float32(180.0))
+        assert ops[1][1][0] == np.float32(np.sin(np.float64(rad))) or abs(ops[1][1][0] - np.sin(float(rad))) < 1e-7
+        assert abs(ops[1][1][1] - np.cos(float(rad))) < 1e-7
+
+
+def test_emit_errors():
+    b = rtw.cuda_backend()
+    with b.new_scene() as s:
+        with pytest.raises(rtw.RtwError, match="bad"):
+            s.sphere((0, 0, 0), 1.0, 0)                      # no such material
+        with pytest.raises(rtw.RtwError, match="fuzz"):
+            s.metal(.5, .5, .5, 1.5)                          # assert!(fuzz <= 1.0), material.rs:71
+        with pytest.raises(rtw.RtwError, match="texture"):
+            s.lambertian(7)
+        with pytest.raises(rtw.RtwError, match="no open transform"):
+            s.pop_transform()
+        s.push_translation((1, 2, 3))
+        with pytest.raises(rtw.RtwError, match="empty instance"):
+            s.pop_transform()
+        with pytest.raises(rtw.RtwError, match="unbalanced"):
+            s.build()
+    with b.new_scene() as s:
+        with pytest.raises(rtw.RtwError, match="empty scene"):
+            s.build()
+        m = s.lambertian_rgb(.5, .5, .5)
+        for _ in range(8):
+            s.push_rotation_y(1.0)
+        with pytest.raises(rtw.RtwError, match="nesting"):
+            s.push_rotation_y(1.0)
+        with pytest.raises(rtw.RtwError, match="not built"):
+            s.trace_closest(rtw.make_rays([[0, 0, 0]], [[0, 0, 1]]))
+
+
+@pytest.mark.skipif(HAS_GPU, reason="checks the no-GPU failure mode")
+def test_no_gpu_fails_loudly_no_fallback():
+    b = rtw.cuda_backend()
+    assert b.device_count() < 0 and "CUDA" in b.last_error()
+    with b.new_scene() as s:
+        s.sphere((0, 0, 0), 1.0, s.lambertian_rgb(.5, .5, .5))
+        with pytest.raises(rtw.RtwError, match="no CPU fallback"):
+            s.build()
+    with pytest.raises(rtw.RtwError):
+        rtw.Scene.from_name(b, "cornell-box", 1.0)

@@ -1,0 +1,213 @@
+"""GPU parity tests: the CUDA backend (through its C ABI) against the CPU oracle on identical inputs.
+
+Bar (BASELINE.json north_star): closest-hit primitive ids bit-exact except documented exact ties (none
+occur: the backend implements the reference list's "last tested wins" rule exactly); hit t / p / normal
+bit-exact (stronger than the 1e-5 asked); uv within 1e-5 (CUDA acosf/atan2f differ from glibc by <= 2 ulp);
+images bit-exact where no libm call is on the path (Cornell box), RMSE-bounded otherwise.
+"""
+import numpy as np
+import pytest
+
+import raytracer_weekend_b200 as rtw
+from conftest import bits
+
+pytestmark = pytest.mark.gpu
+
+SCENES = [("cornell-box", 1.0), ("jumpy-balls", 16 / 9), ("cow-lambert-metal", 16 / 9), ("wavefront-cow-obj", 16 / 9),
+          ("simple-triangle", 16 / 9), ("two-spheres", 16 / 9), ("two-perlin-spheres", 16 / 9), ("earth", 16 / 9),
+          ("simple-light", 16 / 9), ("monument-earth", 16 / 9), ("stress:3000:400", 16 / 9)]
+
+
+def assert_hits_equal(hg, ho, what):
+    same_id = hg["prim_id"] == ho["prim_id"]
+    assert same_id.all(), f"{what}: {np.count_nonzero(~same_id)} closest-hit id mismatches of {len(hg)}"
+    assert np.array_equal(bits(hg["t"]), bits(ho["t"])), f"{what}: t differs"
+    assert np.array_equal(bits(hg["p"]), bits(ho["p"])), f"{what}: p differs"
+    assert np.array_equal(bits(hg["normal"]), bits(ho["normal"])), f"{what}: normal differs"
+    assert np.array_equal(hg["front_face"], ho["front_face"]), f"{what}: front_face differs"
+    assert np.array_equal(hg["material_id"], ho["material_id"]), f"{what}: material differs"
+    np.testing.assert_allclose(hg["u"], ho["u"], rtol=1e-5, atol=2e-6, err_msg=what)   # tolerance of the north star
+    np.testing.assert_allclose(hg["v"], ho["v"], rtol=1e-5, atol=2e-6, err_msg=what)
+
+
+def test_smoke_entry():
+    import __graft_entry__ as g
+
+    g.smoke()
+
+
+@pytest.mark.parametrize("scene,aspect", SCENES)
+def test_trace_parity_on_captured_ray_batches(gpu, oracle, scene, aspect):
+    w, h = 192, int(round(192 / aspect))
+    with rtw.Scene.from_name(gpu, scene, w / h, seed=1) as sg, rtw.Scene.from_name(oracle, scene, w / h, seed=1) as so:
+        cam = sg.cameras[0]
+        for bounce in (0, 1, 2, 4):
+            rays = oracle.capture_rays(so, cam, w, h, 11, bounce, bounce)  # sample index = bounce: different jitter
+            ho = so.trace_closest(rays)
+            assert_hits_equal(sg.trace_closest(rays, rtw.RTW_TRACE_BVH), ho, f"{scene} bounce {bounce} LBVH")
+            assert_hits_equal(sg.trace_closest(rays, rtw.RTW_TRACE_BRUTE), ho, f"{scene} bounce {bounce} brute force")
+
+
+def test_trace_parity_on_adversarial_rays(gpu, oracle):
+    """axis-aligned rays, rays starting on surfaces, along box edges and diagonals (exact-t ties), finite windows"""
+    rs = np.random.RandomState(5)
+    with rtw.Scene.from_name(gpu, "cornell-box", 1.0) as sg, rtw.Scene.from_name(oracle, "cornell-box", 1.0) as so:
+        o = rs.uniform(1, 554, (20000, 3)).astype(np.float32)
+        d = rs.uniform(-1, 1, (20000, 3)).astype(np.float32)
+        d[:4000, 0] = 0                                    # 1/d = inf on one axis
+        d[4000:6000] = np.eye(3, dtype=np.float32)[rs.randint(0, 3, 2000)] * rs.choice([-1, 1], (2000, 1))
+        o[6000:8000, 1] = 0.0                              # origins on the floor plane
+        o[8000:9000] = (278, 278, -800)
+        d[8000:9000] = np.array([[0, 0, 1]], np.float32) + rs.uniform(-.35, .35, (1000, 3)).astype(np.float32) * [1, 1, 0]
+        o[9000:9500] = (0, 0, 0)                           # corner to corner
+        d[9000:9500] = (555, 555, 555)
+        rays = rtw.make_rays(o, d)
+        rays["t_max"][10000:12000] = rs.uniform(1, 800, 2000)
+        rays["t_min"][12000:13000] = rs.uniform(0, 300, 1000)
+        keep = np.isfinite(so.trace_closest(rays)["t"])    # in-plane NaN hits are undefined behaviour of the reference
+        ho = so.trace_closest(rays[keep])
+        assert_hits_equal(sg.trace_closest(rays[keep]), ho, "cornell adversarial")
+    with gpu.new_scene() as sg, oracle.new_scene() as so:   # stacked coincident / touching primitives
+        for s in (sg, so):
+            m = s.lambertian_rgb(.5, .5, .5)
+            for _ in range(3):
+                s.xy_rect(0, 1, 0, 1, 2, m)
+            s.cuboid((0, 0, 3), (1, 1, 4), m)
+            s.cuboid((1, 0, 3), (2, 1, 4), m)               # shares the x = 1 face
+            s.sphere((0.5, 0.5, 6), 0.5, m)
+            s.sphere((0.5, 0.5, 7), 0.5, m)                 # touches the first sphere at z = 6.5
+            s.triangles([[0, 0, 8, 1, 0, 8, 0, 1, 8], [1, 0, 8, 1, 1, 8, 0, 1, 8]], m)  # shared diagonal edge
+            s.build()
+        o = rs.uniform(-.5, 2.5, (30000, 3)).astype(np.float32) * [1, 1, 0] + [0, 0, -1]
+        d = np.tile(np.array([[0, 0, 1]], np.float32), (30000, 1))
+        o[:5000, :2] = np.round(o[:5000, :2] * 4) / 4      # lattice points: hit edges and corners exactly
+        o[5000:6000] = (3, .5, 3.5)
+        d[5000:6000] = (-1, 0, 0)
+        rays = rtw.make_rays(o, d)
+        ho = so.trace_closest(rays)
+        hg = sg.trace_closest(rays)
+        assert_hits_equal(hg, ho, "coincident primitives")
+        assert (ho["prim_id"][np.isclose(ho["t"], 3.0)] == 2).any()   # the last of the three coincident rects wins
+
+
+def test_render_cornell_bit_exact(gpu, oracle):
+    with rtw.Scene.from_name(gpu, "cornell-box", 1.0) as sg, rtw.Scene.from_name(oracle, "cornell-box", 1.0) as so:
+        cam = sg.cameras[0]
+        for w, h, spp, slices, pool in ((96, 96, 12, 1, 0), (96, 96, 12, 4, 4096), (128, 64, 7, 3, 1 << 16), (33, 47, 5, 5, 96)):
+            p = sg.params(w, h, spp, seed=5, slices=slices, pool_size=pool)
+            ag, stg = sg.render(cam, p)
+            ao, sto = so.render(cam, p)
+            assert stg.segments == sto.segments and stg.paths == sto.paths == w * h * spp
+            assert np.array_equal(bits(ag), bits(ao)), (w, h, spp, slices, pool)
+
+
+def test_render_cornell_full_resolution_bit_exact(gpu, oracle):
+    """BASELINE config C2's frame size (800x800) at 2 spp against the oracle, every pixel bit for bit."""
+    with rtw.Scene.from_name(gpu, "cornell-box", 1.0) as sg, rtw.Scene.from_name(oracle, "cornell-box", 1.0) as so:
+        p = sg.params(800, 800, 2, seed=2024, slices=2)
+        ag, stg = sg.render(sg.cameras[0], p)
+        ao, sto = so.render(so.cameras[0], p)
+        assert stg.segments == sto.segments
+        assert np.array_equal(bits(ag), bits(ao))
+
+
+@pytest.mark.parametrize("scene,aspect", [("jumpy-balls", 16 / 9), ("cow-lambert-metal", 16 / 9), ("monument-earth", 16 / 9),
+                                          ("two-perlin-spheres", 16 / 9), ("simple-light", 16 / 9), ("stress:3000:400", 16 / 9)])
+def test_render_statistical_parity(gpu, oracle, scene, aspect):
+    """Scenes with sinf / acosf / atan2f on the path: same stream, same control flow except where a
+    <= 2 ulp libm difference flips a checker cell / texel / Perlin value.  Stated bound: at equal spp the
+    images agree to RMSE <= 2% of the mean radiance and >= 97% of the pixels are bit-identical."""
+    w, h, spp = 160, int(round(160 / aspect)), 8
+    with rtw.Scene.from_name(gpu, scene, w / h, seed=1) as sg, rtw.Scene.from_name(oracle, scene, w / h, seed=1) as so:
+        p = sg.params(w, h, spp, seed=77, slices=2)
+        ag, stg = sg.render(sg.cameras[0], p)
+        ao, sto = so.render(so.cameras[0], p)
+        assert abs(int(stg.segments) - int(sto.segments)) <= 0.01 * sto.segments
+        same = (bits(ag) == bits(ao)).all(axis=2).mean()
+        rmse = float(np.sqrt(np.mean((ag - ao) ** 2)))
+        assert rmse <= 0.02 * float(np.mean(ao)) + 1e-6, (rmse, float(np.mean(ao)))
+        assert same >= 0.97, same
+
+
+def test_image_is_independent_of_pool_partition_and_counters(gpu):
+    with rtw.Scene.from_name(gpu, "jumpy-balls", 16 / 9, seed=3) as s:
+        cam = s.cameras[0]
+        w, h, spp = 200, 112, 6
+        ref, st0 = s.render(cam, s.params(w, h, spp, seed=9, slices=3))
+        for pool in (64, 5000, 1 << 18):
+            a, st = s.render(cam, s.params(w, h, spp, seed=9, slices=3, pool_size=pool))
+            assert np.array_equal(bits(a), bits(ref)) and st.segments == st0.segments
+        a, st = s.render(cam, s.params(w, h, spp, seed=9, slices=3, flags=rtw.RTW_RENDER_COUNT_TRAVERSAL | rtw.RTW_RENDER_TIME_KERNELS))
+        assert np.array_equal(bits(a), bits(ref))
+        assert st.node_visits > st.segments and st.prim_tests > 0 and st.prim_bytes > 0 and st.ms_traverse > 0
+        for parts, ts in ((2, 32), (3, 16), (8, 32)):
+            total = np.zeros_like(ref)
+            seg = 0
+            for r in range(parts):
+                a, st = s.render(cam, s.params(w, h, spp, seed=9, slices=3, part_rank=r, part_count=parts, tile_size=ts))
+                assert np.count_nonzero(total[a != 0]) == 0       # disjoint pixel sets
+                total += a
+                seg += st.segments
+            assert np.array_equal(bits(total), bits(ref)) and seg == st0.segments
+        a, _ = s.render(cam, s.params(w, h, spp, seed=9, slices=3, sample_begin=0, sample_end=2))
+        b, _ = s.render(cam, s.params(w, h, spp, seed=9, slices=3, sample_begin=2, sample_end=6))
+        np.testing.assert_allclose(a + b, ref, rtol=2e-6, atol=1e-7)   # sample slices: same samples, other summation tree
+        z, st = s.render(cam, s.params(w, h, spp, seed=9, sample_begin=3, sample_end=3))
+        assert st.segments == 0 and not z.any()
+
+
+def test_bvh_structure(gpu):
+    """every primitive slot is reachable exactly once; every child box lies inside its parent's; leaves are
+    contiguous slot ranges; the instance / type order inside a leaf is sorted"""
+    for scene in ("cornell-box", "cow-lambert-metal", "jumpy-balls", "stress:2000:300"):
+        with rtw.Scene.from_name(gpu, scene, 16 / 9, seed=1) as s:
+            nodes, slot_ids, root = s.get_bvh()
+            n = s.num_prims
+            assert sorted(slot_ids.tolist()) == list(range(n))
+            seen = np.zeros(n, np.int32)
+            stack = [(0, root[:3], root[3:])]
+            visited = 0
+            while stack:
+                pair, lo, hi = stack.pop()
+                visited += 1
+                for rec in nodes[2 * pair:2 * pair + 2]:
+                    if rec["meta"] == 0 and rec["link"] < 0 and np.isinf(rec["bmin"]).any():
+                        continue                                       # the empty sibling of a flat scene
+                    assert (rec["bmin"] >= lo - 1e-6 * np.abs(lo)).all() and (rec["bmax"] <= hi + 1e-6 * np.abs(hi)).all()
+                    if rec["link"] >= 0:
+                        stack.append((int(rec["link"]), rec["bmin"], rec["bmax"]))
+                    else:
+                        first, cnt = ~int(rec["link"]), int(rec["meta"])
+                        assert 1 <= cnt <= 32 and first + cnt <= n
+                        seen[first:first + cnt] += 1
+                        metas = [s.prim_info(int(i))[1] * 8 + s.prim_info(int(i))[0] for i in slot_ids[first:first + cnt]]
+                        assert metas == sorted(metas)
+            assert (seen == 1).all(), scene
+            assert s.build_stats.num_prims == n and s.build_stats.max_depth < 90
+
+
+def test_resolve_rgb8_matches_reference_tonemap(gpu, oracle):
+    rs = np.random.RandomState(0)
+    acc = (rs.uniform(0, 3, (64, 48, 3)) ** 3).astype(np.float32) * 16
+    acc[0, 0] = (np.nan, -1.0, 1e30)
+    with gpu.new_scene() as sg, oracle.new_scene() as so:
+        assert np.array_equal(sg.resolve_rgb8(acc, 16), so.resolve_rgb8(acc, 16))
+
+
+def test_state_errors(gpu):
+    with gpu.new_scene() as s:
+        m = s.lambertian_rgb(.5, .5, .5)
+        s.sphere((0, 0, -2), 1.0, m)
+        with pytest.raises(rtw.RtwError, match="not built"):
+            s.render(rtw.camera_new((0, 0, 0), (0, 0, -1), (0, 1, 0), 40, 1.0), s.params(8, 8, 1))
+        s.build()
+        with pytest.raises(rtw.RtwError, match="already built"):
+            s.sphere((0, 0, -2), 1.0, m)
+        cam = rtw.camera_new((0, 0, 0), (0, 0, -1), (0, 1, 0), 40, 1.0)
+        with pytest.raises(rtw.RtwError, match=">= 2"):
+            s.render(cam, s.params(1, 8, 1))
+        with pytest.raises(rtw.RtwError, match="part_rank"):
+            s.render(cam, s.params(8, 8, 1, part_rank=3, part_count=2))
+        a, st = s.render(cam, s.params(8, 8, 2, background=(0.5, 0.25, 1.0)))   # single primitive scene
+        assert st.paths == 128 and a.shape == (8, 8, 3) and np.isfinite(a).all() and a.max() > 0
+        assert s.trace_closest(np.zeros(0, rtw.RAY_DTYPE)).shape == (0,)        # empty batch

@@ -5,7 +5,8 @@
 BASELINE.json's configs name are converted ONCE, here, into two trivial binary formats that both
 the C++ host library and numpy read:
 
-  .rtwm  mesh   : "RTWM" u32 version=1, u32 ntris, u32 flags (1 = normals, 2 = uvs),
+  .rtwm  mesh   : "RTWM" u32 version=1, u32 ntris, u32 flags (1 = normals, 2 = uvs, 4 = the OBJ names
+                  materials with usemtl — the fixture does not carry them),
                   f32 verts[ntris*9], f32 normals[ntris*9] (if flag 1), f32 uvs[ntris*6] (if flag 2)
                   One record per face in FILE ORDER (= canonical primitive order, triangular.rs:170-218);
                   polygons are fan-triangulated like the wavefront_obj crate does.
@@ -24,6 +25,7 @@ import numpy as np
 def parse_obj(path):
     v, vt, vn = [], [], []
     tris = []  # per triangle: 3 x (vi, ti or None, ni or None)
+    uses_mtl = False
     with open(path) as f:
         for line in f:
             parts = line.split()
@@ -36,6 +38,8 @@ def parse_obj(path):
                 vt.append(vals + [0.0] * (2 - len(vals)))
             elif parts[0] == "vn":
                 vn.append([float(x) for x in parts[1:4]])
+            elif parts[0] == "usemtl":
+                uses_mtl = True
             elif parts[0] == "f":
                 corners = []
                 for c in parts[1:]:
@@ -53,10 +57,10 @@ def parse_obj(path):
                     raise ValueError("points / lines panic in the reference (triangular.rs:186-191)")
                 for k in range(2, len(corners)):
                     tris.append((corners[0], corners[k - 1], corners[k]))
-    return np.array(v, np.float64), np.array(vt, np.float64), np.array(vn, np.float64), tris
+    return np.array(v, np.float64), np.array(vt, np.float64), np.array(vn, np.float64), tris, uses_mtl
 
 
-def write_mesh(path, v, vt, vn, tris):
+def write_mesh(path, v, vt, vn, tris, uses_mtl):
     n = len(tris)
     has_n = all(c[2] is not None for t in tris for c in t)
     has_t = all(c[1] is not None for t in tris for c in t)
@@ -70,7 +74,7 @@ def write_mesh(path, v, vt, vn, tris):
                 norms[i, 3 * k:3 * k + 3] = vn[ni].astype(np.float32)
             if has_t:
                 uvs[i, 2 * k:2 * k + 2] = vt[ti].astype(np.float32)
-    flags = (1 if has_n else 0) | (2 if has_t else 0)
+    flags = (1 if has_n else 0) | (2 if has_t else 0) | (4 if uses_mtl else 0)
     with open(path, "wb") as f:
         f.write(b"RTWM" + struct.pack("<III", 1, n, flags))
         f.write(verts.tobytes())
