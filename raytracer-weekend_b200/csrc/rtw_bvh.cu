@@ -442,7 +442,12 @@ __global__ void k_sort_leaf_ranges(uint32_t n_internal, const uint32_t* __restri
                                    const uint32_t* __restrict__ meta, uint32_t* __restrict__ vals) {
   uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_internal || !collapsed[p]) return;
-  if (p != 0 && collapsed[node_parent[p] >> 1]) return;
+  // final = no ancestor collapsed.  (Checking only the parent is not enough: a grandparent may collapse
+  // although the parent did not, and two threads would then sort overlapping ranges concurrently.)
+  for (uint32_t q = p; q != 0;) {
+    q = node_parent[q] >> 1;
+    if (collapsed[q]) return;
+  }
   uint2 rg = node_range[p];
   for (uint32_t i = 1; i < rg.y; ++i) {
     uint32_t v = vals[rg.x + i];
