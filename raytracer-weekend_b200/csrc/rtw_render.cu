@@ -67,7 +67,8 @@ struct WaveHost {
   std::vector<void*> allocs;
   uint32_t pool = 0;
   size_t partial_elems = 0;
-  WaveCtl* pinned_ctl = nullptr;
+  WaveCtl* pinned_ctl = nullptr;   // 2 entries: ring for the lagging termination check
+  cudaStream_t stream = nullptr;    // internal non-blocking stream (graph capture needs a non-legacy stream)
   int blocks_traverse = 0, blocks_traverse_count = 0, blocks_shade = 0;
 };
 
@@ -355,6 +356,7 @@ void free_wave(rtw_scene* s) {
   if (!wh) return;
   wave_release(wh);
   if (wh->pinned_ctl) cudaFreeHost(wh->pinned_ctl);
+  if (wh->stream) cudaStreamDestroy(wh->stream);
   delete wh;
   s->wave = nullptr;
 }
@@ -430,7 +432,8 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
   if (!wh) {
     wh = new WaveHost();
     s->wave = wh;
-    RTW_CUDA_TRY(cudaMallocHost((void**)&wh->pinned_ctl, sizeof(WaveCtl)));
+    RTW_CUDA_TRY(cudaMallocHost((void**)&wh->pinned_ctl, 2 * sizeof(WaveCtl)));
+    RTW_CUDA_TRY(cudaStreamCreateWithFlags(&wh->stream, cudaStreamNonBlocking));
     int nb = 0;
     RTW_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wave_traverse<false>, 128, 0));
     wh->blocks_traverse = std::max(nb, 1) * s->num_sms;
@@ -461,7 +464,14 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
 
   const bool count_trav = (p->flags & RTW_RENDER_COUNT_TRAVERSAL) != 0;
   const bool time_kernels = (p->flags & 2u) != 0;
-  cudaEvent_t ev_begin, ev_end;
+  // All work runs on an internal stream ordered after the caller's stream; the call returns only after
+  // that stream has drained, so the caller's stream order is preserved on both sides.
+  cudaStream_t user_stream = st;
+  st = wh->stream;
+  cudaEvent_t ev_in, ev_begin, ev_end;
+  RTW_CUDA_TRY(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
+  RTW_CUDA_TRY(cudaEventRecord(ev_in, user_stream));
+  RTW_CUDA_TRY(cudaStreamWaitEvent(st, ev_in, 0));
   RTW_CUDA_TRY(cudaEventCreate(&ev_begin));
   RTW_CUDA_TRY(cudaEventCreate(&ev_end));
   std::vector<cudaEvent_t> kev;  // begin/end pairs: traverse, shade, traverse, shade ...
@@ -473,32 +483,64 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
   if (f.n_items > 0) {
     k_wave_init<<<(pool + 127) / 128, 128, 0, st>>>(s->dev, f, w);
     launches++;
-    uint32_t parity = 0;
-    const int batch = 8;
-    for (;;) {
-      for (int b = 0; b < batch; ++b) {
-        if (time_kernels) {
-          cudaEvent_t e4[4];
-          for (auto& e : e4) { RTW_CUDA_TRY(cudaEventCreate(&e)); kev.push_back(e); }
-          RTW_CUDA_TRY(cudaEventRecord(e4[0], st));
-        }
-        if (count_trav)
-          k_wave_traverse<true><<<wh->blocks_traverse_count, 128, 0, st>>>(s->dev, w, parity);
-        else
-          k_wave_traverse<false><<<wh->blocks_traverse, 128, 0, st>>>(s->dev, w, parity);
-        if (time_kernels) {
-          RTW_CUDA_TRY(cudaEventRecord(kev[kev.size() - 3], st));
-          RTW_CUDA_TRY(cudaEventRecord(kev[kev.size() - 2], st));
-        }
-        k_wave_shade<<<wh->blocks_shade, 128, 0, st>>>(s->dev, f, w, d_accum, parity);
-        if (time_kernels) RTW_CUDA_TRY(cudaEventRecord(kev[kev.size() - 1], st));
-        parity ^= 1;
-        launches += 2;
-        iterations++;
+    if (!count_trav && !time_kernels) {
+      // ---- product path: a CUDA graph of BATCH iterations, launched back to back; the host looks at the
+      // live count of batch i-1 while batch i is already running (an empty extra batch costs ~50 us).
+      const int BATCH = 16;  // even: the queue parity is back to 0 after every batch
+      cudaGraph_t graph = nullptr;
+      cudaGraphExec_t exec = nullptr;
+      RTW_CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      for (int b = 0; b < BATCH; ++b) {
+        k_wave_traverse<false><<<wh->blocks_traverse, 128, 0, st>>>(s->dev, w, (uint32_t)(b & 1));
+        k_wave_shade<<<wh->blocks_shade, 128, 0, st>>>(s->dev, f, w, d_accum, (uint32_t)(b & 1));
       }
-      RTW_CUDA_TRY(cudaMemcpyAsync(wh->pinned_ctl, w.ctl, sizeof(WaveCtl), cudaMemcpyDeviceToHost, st));
-      RTW_CUDA_TRY(cudaStreamSynchronize(st));
-      if (wh->pinned_ctl->count[parity] == 0) break;
+      RTW_CUDA_TRY(cudaStreamEndCapture(st, &graph));
+      RTW_CUDA_TRY(cudaGraphInstantiate(&exec, graph, 0));
+      cudaEvent_t ring_ev[2];
+      for (auto& e : ring_ev) RTW_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      for (uint32_t i = 0;; ++i) {
+        RTW_CUDA_TRY(cudaGraphLaunch(exec, st));
+        RTW_CUDA_TRY(cudaMemcpyAsync(&wh->pinned_ctl[i & 1], w.ctl, sizeof(WaveCtl), cudaMemcpyDeviceToHost, st));
+        RTW_CUDA_TRY(cudaEventRecord(ring_ev[i & 1], st));
+        launches += 2 * BATCH;
+        iterations += BATCH;
+        if (i >= 1) {
+          RTW_CUDA_TRY(cudaEventSynchronize(ring_ev[(i - 1) & 1]));
+          if (wh->pinned_ctl[(i - 1) & 1].count[0] == 0) break;
+        }
+      }
+      for (auto& e : ring_ev) cudaEventDestroy(e);
+      cudaGraphExecDestroy(exec);
+      cudaGraphDestroy(graph);
+    } else {
+      // ---- instrumented path (traversal counters / per-kernel CUDA events): plain launches
+      uint32_t parity = 0;
+      const int batch = 8;
+      for (;;) {
+        for (int b = 0; b < batch; ++b) {
+          if (time_kernels) {
+            cudaEvent_t e4[4];
+            for (auto& e : e4) { RTW_CUDA_TRY(cudaEventCreate(&e)); kev.push_back(e); }
+            RTW_CUDA_TRY(cudaEventRecord(e4[0], st));
+          }
+          if (count_trav)
+            k_wave_traverse<true><<<wh->blocks_traverse_count, 128, 0, st>>>(s->dev, w, parity);
+          else
+            k_wave_traverse<false><<<wh->blocks_traverse, 128, 0, st>>>(s->dev, w, parity);
+          if (time_kernels) {
+            RTW_CUDA_TRY(cudaEventRecord(kev[kev.size() - 3], st));
+            RTW_CUDA_TRY(cudaEventRecord(kev[kev.size() - 2], st));
+          }
+          k_wave_shade<<<wh->blocks_shade, 128, 0, st>>>(s->dev, f, w, d_accum, parity);
+          if (time_kernels) RTW_CUDA_TRY(cudaEventRecord(kev[kev.size() - 1], st));
+          parity ^= 1;
+          launches += 2;
+          iterations++;
+        }
+        RTW_CUDA_TRY(cudaMemcpyAsync(wh->pinned_ctl, w.ctl, sizeof(WaveCtl), cudaMemcpyDeviceToHost, st));
+        RTW_CUDA_TRY(cudaStreamSynchronize(st));
+        if (wh->pinned_ctl->count[parity] == 0) break;
+      }
     }
   }
   if (slices > 1 || f.n_items == 0) {
@@ -514,6 +556,7 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
   RTW_CUDA_TRY(cudaStreamSynchronize(st));
   float ms = 0.f;
   cudaEventElapsedTime(&ms, ev_begin, ev_end);
+  cudaEventDestroy(ev_in);
   cudaEventDestroy(ev_begin);
   cudaEventDestroy(ev_end);
   float ms_t = 0.f, ms_s = 0.f;
