@@ -20,7 +20,7 @@ import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(PKG_DIR)
-CUDA_LIB = os.path.join(PKG_DIR, "lib", "librtw_cuda.so")
+CUDA_LIB = os.environ.get("RTW_CUDA_LIB") or os.path.join(PKG_DIR, "lib", "librtw_cuda.so")  # env override: A/B builds
 HOST_LIB = os.path.join(PKG_DIR, "lib", "librtw_host.so")
 ASSET_DIR = os.path.join(REPO_ROOT, "assets")
 

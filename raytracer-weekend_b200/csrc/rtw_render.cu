@@ -14,6 +14,7 @@
 //   time from a device-side cursor, so no launch parameter depends on the live count and the host
 //   only synchronises every few iterations to learn whether the queue is empty.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -24,7 +25,9 @@ namespace rtw {
 
 namespace {
 
-struct WaveCtl {
+#define RTW_MAX_SUBPOOLS 4
+
+struct WaveCtl {           // one per sub-pool (+ one extra whose item_cursor is the shared work-item cursor)
   unsigned long long item_cursor;
   unsigned long long segments;
   unsigned long long paths;
@@ -46,7 +49,9 @@ struct WaveDev {
   uint4* state;     // pixel index (row*w+col), sample, sample_end, bounce | slice << 8
   uint32_t* queue[2];
   float4* partial;  // [slices][w*h] slice sums (slices > 1)
-  WaveCtl* ctl;
+  WaveCtl* ctl;                      // this sub-pool's counters
+  unsigned long long* item_cursor;   // shared by all sub-pools
+  uint32_t slot_base, slot_count;    // this sub-pool's slots: [slot_base, slot_base + slot_count)
 };
 
 struct FrameDev {
@@ -67,8 +72,9 @@ struct WaveHost {
   std::vector<void*> allocs;
   uint32_t pool = 0;
   size_t partial_elems = 0;
-  WaveCtl* pinned_ctl = nullptr;   // 2 entries: ring for the lagging termination check
+  WaveCtl* pinned_ctl = nullptr;   // [RTW_MAX_SUBPOOLS][2]: ring for the lagging termination check
   cudaStream_t stream = nullptr;    // internal non-blocking stream (graph capture needs a non-legacy stream)
+  cudaStream_t pool_stream[RTW_MAX_SUBPOOLS] = {};
   int blocks_traverse = 0, blocks_traverse_count = 0, blocks_shade = 0;
 };
 
@@ -99,14 +105,14 @@ __device__ __forceinline__ bool decode_item(const FrameDev& f, unsigned long lon
 
 // Warp-cooperative fetch: every lane with `need` gets a valid item or learns that none are left.
 // Must be called by all 32 lanes.
-__device__ __forceinline__ bool fetch_item(const FrameDev& f, WaveCtl* ctl, bool need, Item& it) {
+__device__ __forceinline__ bool fetch_item(const FrameDev& f, unsigned long long* item_cursor, bool need, Item& it) {
   const uint32_t lane = threadIdx.x & 31;
   bool got = false;
   for (;;) {
     uint32_t m = __ballot_sync(0xffffffffu, need && !got);
     if (m == 0) break;
     unsigned long long base = 0;
-    if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(&ctl->item_cursor, (unsigned long long)__popc(m));
+    if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(item_cursor, (unsigned long long)__popc(m));
     base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
     if (base >= f.n_items) break;  // exhausted (cursor may overshoot; harmless)
     if (need && !got) {
@@ -143,9 +149,10 @@ __device__ __forceinline__ void queue_push(uint32_t* queue, uint32_t* count, boo
 }
 
 __global__ void k_wave_init(SceneDev sc, FrameDev f, WaveDev w) {
-  uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;  // block = 128 threads: whole warps reach the ballots
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;  // block = 128 threads: whole warps reach the ballots
+  const uint32_t slot = w.slot_base + tid;
   Item it;
-  bool got = fetch_item(f, w.ctl, slot < f.pool, it);
+  bool got = fetch_item(f, w.item_cursor, tid < w.slot_count, it);
   if (got) {
     start_path(f, w, slot, it);
     w.sum[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -287,7 +294,7 @@ __global__ void __launch_bounds__(128) k_wave_shade(SceneDev sc, FrameDev f, Wav
         }
       }
     }
-    if (fetch_item(f, ctl, need_item, it)) {
+    if (fetch_item(f, w.item_cursor, need_item, it)) {
       w.sum[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
       start_path(f, w, slot, it);
       new_paths++;
@@ -357,6 +364,8 @@ void free_wave(rtw_scene* s) {
   wave_release(wh);
   if (wh->pinned_ctl) cudaFreeHost(wh->pinned_ctl);
   if (wh->stream) cudaStreamDestroy(wh->stream);
+  for (auto& ps : wh->pool_stream)
+    if (ps) cudaStreamDestroy(ps);
   delete wh;
   s->wave = nullptr;
 }
@@ -412,7 +421,11 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
   const uint32_t owned_tiles = f.tiles_total > f.part_rank ? (f.tiles_total - f.part_rank + f.part_count - 1) / f.part_count : 0;
   f.pix_per_slice = (unsigned long long)owned_tiles * f.tile_size * f.tile_size;
 
-  uint32_t pool = p->pool_size ? p->pool_size : (1u << 20);
+  // Default pool (measured, profiles/r01_pool_sweep.txt): a flat scene (one converged primitive loop) peaks at
+  // 2^20 slots — its 88 B/slot state then stays L2-resident; a scene with a hierarchy amortises the fixed
+  // ramp/tail cost of the persistent kernels better with 2^21 (2^22 for frames above 4 Mpixel).
+  uint32_t pool = p->pool_size ? p->pool_size
+                               : ((s->dev.num_prims <= 32) ? (1u << 20) : (npix > (4u << 20) ? (1u << 22) : (1u << 21)));
   pool = (pool + 31u) & ~31u;
   uint32_t slices = p->slices;
   if (slices == 0) {  // enough items that the last ones to finish are a small fraction of the frame
@@ -432,8 +445,9 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
   if (!wh) {
     wh = new WaveHost();
     s->wave = wh;
-    RTW_CUDA_TRY(cudaMallocHost((void**)&wh->pinned_ctl, 2 * sizeof(WaveCtl)));
+    RTW_CUDA_TRY(cudaMallocHost((void**)&wh->pinned_ctl, 2 * (RTW_MAX_SUBPOOLS + 1) * sizeof(WaveCtl)));
     RTW_CUDA_TRY(cudaStreamCreateWithFlags(&wh->stream, cudaStreamNonBlocking));
+    for (auto& ps : wh->pool_stream) RTW_CUDA_TRY(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
     int nb = 0;
     RTW_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wave_traverse<false>, 128, 0));
     wh->blocks_traverse = std::max(nb, 1) * s->num_sms;
@@ -456,7 +470,7 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
     if ((rc = wave_alloc(wh, &w.queue[0], pool))) return rc;
     if ((rc = wave_alloc(wh, &w.queue[1], pool))) return rc;
     if ((rc = wave_alloc(wh, &w.partial, partial_elems))) return rc;
-    if ((rc = wave_alloc(wh, &w.ctl, 1))) return rc;
+    if ((rc = wave_alloc(wh, &w.ctl, RTW_MAX_SUBPOOLS + 1))) return rc;
     wh->pool = pool;
     wh->partial_elems = partial_elems;
   }
@@ -477,43 +491,93 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
   std::vector<cudaEvent_t> kev;  // begin/end pairs: traverse, shade, traverse, shade ...
   uint32_t launches = 0, iterations = 0;
 
+  // Sub-pools: the slot range is split into K independent halves/quarters, each with its own queues,
+  // counters and stream.  Their kernels depend only on their own predecessor, so the ramp-up and the
+  // tail of one sub-pool's persistent kernel (~15 us per launch, measured by the pool-size sweep in
+  // profiles/) overlap the body of another's, and latency-bound shading overlaps issue-bound traversal.
+  uint32_t K = 1;
+  if (!count_trav && !time_kernels && pool >= (1u << 16)) {
+    K = 2;
+    if (const char* e = getenv("RTW_SUBPOOLS")) K = (uint32_t)std::min(std::max(atoi(e), 1), RTW_MAX_SUBPOOLS);
+  }
+  WaveDev wk[RTW_MAX_SUBPOOLS];
+  {
+    uint32_t per = ((pool / K) + 31u) & ~31u, base = 0;
+    for (uint32_t k = 0; k < K; ++k) {
+      wk[k] = w;
+      wk[k].ctl = w.ctl + k;
+      wk[k].item_cursor = &w.ctl[RTW_MAX_SUBPOOLS].item_cursor;
+      wk[k].slot_base = base;
+      wk[k].slot_count = (k + 1 == K) ? pool - base : std::min(per, pool - base);
+      wk[k].queue[0] = w.queue[0] + base;
+      wk[k].queue[1] = w.queue[1] + base;
+      base += wk[k].slot_count;
+    }
+  }
   RTW_CUDA_TRY(cudaEventRecord(ev_begin, st));
-  RTW_CUDA_TRY(cudaMemsetAsync(w.ctl, 0, sizeof(WaveCtl), st));
+  RTW_CUDA_TRY(cudaMemsetAsync(w.ctl, 0, (RTW_MAX_SUBPOOLS + 1) * sizeof(WaveCtl), st));
   if (slices == 1) RTW_CUDA_TRY(cudaMemsetAsync(d_accum, 0, npix * 3 * sizeof(float), st));
   if (f.n_items > 0) {
-    k_wave_init<<<(pool + 127) / 128, 128, 0, st>>>(s->dev, f, w);
-    launches++;
     if (!count_trav && !time_kernels) {
-      // ---- product path: a CUDA graph of BATCH iterations, launched back to back; the host looks at the
-      // live count of batch i-1 while batch i is already running (an empty extra batch costs ~50 us).
+      // ---- product path: per sub-pool a CUDA graph of BATCH iterations, launched back to back; the host
+      // looks at the live count of round i-1 while round i is already running.
       const int BATCH = 16;  // even: the queue parity is back to 0 after every batch
-      cudaGraph_t graph = nullptr;
-      cudaGraphExec_t exec = nullptr;
-      RTW_CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-      for (int b = 0; b < BATCH; ++b) {
-        k_wave_traverse<false><<<wh->blocks_traverse, 128, 0, st>>>(s->dev, w, (uint32_t)(b & 1));
-        k_wave_shade<<<wh->blocks_shade, 128, 0, st>>>(s->dev, f, w, d_accum, (uint32_t)(b & 1));
+      cudaEvent_t ev_fork, ev_join[RTW_MAX_SUBPOOLS], ring_ev[RTW_MAX_SUBPOOLS][2];
+      cudaGraph_t graph[RTW_MAX_SUBPOOLS];
+      cudaGraphExec_t exec[RTW_MAX_SUBPOOLS];
+      RTW_CUDA_TRY(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+      RTW_CUDA_TRY(cudaEventRecord(ev_fork, st));
+      for (uint32_t k = 0; k < K; ++k) {
+        cudaStream_t sk = wh->pool_stream[k];
+        RTW_CUDA_TRY(cudaEventCreateWithFlags(&ev_join[k], cudaEventDisableTiming));
+        for (auto& e : ring_ev[k]) RTW_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        RTW_CUDA_TRY(cudaStreamWaitEvent(sk, ev_fork, 0));
+        k_wave_init<<<(wk[k].slot_count + 127) / 128, 128, 0, sk>>>(s->dev, f, wk[k]);
+        launches++;
+        RTW_CUDA_TRY(cudaStreamBeginCapture(sk, cudaStreamCaptureModeThreadLocal));
+        for (int b = 0; b < BATCH; ++b) {
+          k_wave_traverse<false><<<wh->blocks_traverse, 128, 0, sk>>>(s->dev, wk[k], (uint32_t)(b & 1));
+          k_wave_shade<<<wh->blocks_shade, 128, 0, sk>>>(s->dev, f, wk[k], d_accum, (uint32_t)(b & 1));
+        }
+        RTW_CUDA_TRY(cudaStreamEndCapture(sk, &graph[k]));
+        RTW_CUDA_TRY(cudaGraphInstantiate(&exec[k], graph[k], 0));
       }
-      RTW_CUDA_TRY(cudaStreamEndCapture(st, &graph));
-      RTW_CUDA_TRY(cudaGraphInstantiate(&exec, graph, 0));
-      cudaEvent_t ring_ev[2];
-      for (auto& e : ring_ev) RTW_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      bool done[RTW_MAX_SUBPOOLS] = {false, false, false, false};
       for (uint32_t i = 0;; ++i) {
-        RTW_CUDA_TRY(cudaGraphLaunch(exec, st));
-        RTW_CUDA_TRY(cudaMemcpyAsync(&wh->pinned_ctl[i & 1], w.ctl, sizeof(WaveCtl), cudaMemcpyDeviceToHost, st));
-        RTW_CUDA_TRY(cudaEventRecord(ring_ev[i & 1], st));
-        launches += 2 * BATCH;
+        for (uint32_t k = 0; k < K; ++k) {
+          if (done[k]) continue;
+          cudaStream_t sk = wh->pool_stream[k];
+          RTW_CUDA_TRY(cudaGraphLaunch(exec[k], sk));
+          RTW_CUDA_TRY(cudaMemcpyAsync(&wh->pinned_ctl[2 * k + (i & 1)], w.ctl + k, sizeof(WaveCtl), cudaMemcpyDeviceToHost, sk));
+          RTW_CUDA_TRY(cudaEventRecord(ring_ev[k][i & 1], sk));
+          launches += 2 * BATCH;
+        }
         iterations += BATCH;
         if (i >= 1) {
-          RTW_CUDA_TRY(cudaEventSynchronize(ring_ev[(i - 1) & 1]));
-          if (wh->pinned_ctl[(i - 1) & 1].count[0] == 0) break;
+          bool all = true;
+          for (uint32_t k = 0; k < K; ++k) {
+            if (!done[k]) {
+              RTW_CUDA_TRY(cudaEventSynchronize(ring_ev[k][(i - 1) & 1]));
+              if (wh->pinned_ctl[2 * k + ((i - 1) & 1)].count[0] == 0) done[k] = true;  // absorbing: no live path, no item left
+            }
+            all = all && done[k];
+          }
+          if (all) break;
         }
       }
-      for (auto& e : ring_ev) cudaEventDestroy(e);
-      cudaGraphExecDestroy(exec);
-      cudaGraphDestroy(graph);
+      for (uint32_t k = 0; k < K; ++k) {
+        RTW_CUDA_TRY(cudaEventRecord(ev_join[k], wh->pool_stream[k]));
+        RTW_CUDA_TRY(cudaStreamWaitEvent(st, ev_join[k], 0));
+        cudaEventDestroy(ev_join[k]);
+        for (auto& e : ring_ev[k]) cudaEventDestroy(e);
+        cudaGraphExecDestroy(exec[k]);
+        cudaGraphDestroy(graph[k]);
+      }
+      cudaEventDestroy(ev_fork);
     } else {
-      // ---- instrumented path (traversal counters / per-kernel CUDA events): plain launches
+      // ---- instrumented path (traversal counters / per-kernel CUDA events): one pool, plain launches
+      k_wave_init<<<(pool + 127) / 128, 128, 0, st>>>(s->dev, f, wk[0]);
+      launches++;
       uint32_t parity = 0;
       const int batch = 8;
       for (;;) {
@@ -524,14 +588,14 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
             RTW_CUDA_TRY(cudaEventRecord(e4[0], st));
           }
           if (count_trav)
-            k_wave_traverse<true><<<wh->blocks_traverse_count, 128, 0, st>>>(s->dev, w, parity);
+            k_wave_traverse<true><<<wh->blocks_traverse_count, 128, 0, st>>>(s->dev, wk[0], parity);
           else
-            k_wave_traverse<false><<<wh->blocks_traverse, 128, 0, st>>>(s->dev, w, parity);
+            k_wave_traverse<false><<<wh->blocks_traverse, 128, 0, st>>>(s->dev, wk[0], parity);
           if (time_kernels) {
             RTW_CUDA_TRY(cudaEventRecord(kev[kev.size() - 3], st));
             RTW_CUDA_TRY(cudaEventRecord(kev[kev.size() - 2], st));
           }
-          k_wave_shade<<<wh->blocks_shade, 128, 0, st>>>(s->dev, f, w, d_accum, parity);
+          k_wave_shade<<<wh->blocks_shade, 128, 0, st>>>(s->dev, f, wk[0], d_accum, parity);
           if (time_kernels) RTW_CUDA_TRY(cudaEventRecord(kev[kev.size() - 1], st));
           parity ^= 1;
           launches += 2;
@@ -552,8 +616,17 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
   }
   RTW_CUDA_TRY(cudaGetLastError());
   RTW_CUDA_TRY(cudaEventRecord(ev_end, st));
-  RTW_CUDA_TRY(cudaMemcpyAsync(wh->pinned_ctl, w.ctl, sizeof(WaveCtl), cudaMemcpyDeviceToHost, st));
+  RTW_CUDA_TRY(cudaMemcpyAsync(wh->pinned_ctl, w.ctl, RTW_MAX_SUBPOOLS * sizeof(WaveCtl), cudaMemcpyDeviceToHost, st));
   RTW_CUDA_TRY(cudaStreamSynchronize(st));
+  WaveCtl total;
+  memset(&total, 0, sizeof(total));
+  for (uint32_t k = 0; k < K; ++k) {
+    total.segments += wh->pinned_ctl[k].segments;
+    total.paths += wh->pinned_ctl[k].paths;
+    total.pairs += wh->pinned_ctl[k].pairs;
+    total.prims += wh->pinned_ctl[k].prims;
+    total.prim_bytes += wh->pinned_ctl[k].prim_bytes;
+  }
   float ms = 0.f;
   cudaEventElapsedTime(&ms, ev_begin, ev_end);
   cudaEventDestroy(ev_in);
@@ -570,11 +643,11 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
   for (auto& e : kev) cudaEventDestroy(e);
   if (stats) {
     memset(stats, 0, sizeof(*stats));
-    stats->segments = wh->pinned_ctl->segments;
-    stats->paths = wh->pinned_ctl->paths;
-    stats->node_visits = wh->pinned_ctl->pairs;
-    stats->prim_tests = wh->pinned_ctl->prims;
-    stats->prim_bytes = wh->pinned_ctl->prim_bytes;
+    stats->segments = total.segments;
+    stats->paths = total.paths;
+    stats->node_visits = total.pairs;
+    stats->prim_tests = total.prims;
+    stats->prim_bytes = total.prim_bytes;
     stats->iterations = iterations;
     stats->launches = launches;
     stats->pool_size = pool;
