@@ -522,6 +522,12 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
       // ---- product path: per sub-pool a CUDA graph of BATCH iterations, launched back to back; the host
       // looks at the live count of round i-1 while round i is already running.
       const int BATCH = 16;  // even: the queue parity is back to 0 after every batch
+      int grid_t = wh->blocks_traverse, grid_s = wh->blocks_shade;
+      if (const char* e = getenv("RTW_GRID_FRAC")) {  // experiment: leave room for the other sub-pool's kernel on every SM
+        float fr = (float)atof(e);
+        grid_t = std::max(s->num_sms, (int)(grid_t * fr));
+        grid_s = std::max(s->num_sms, (int)(grid_s * fr));
+      }
       cudaEvent_t ev_fork, ev_join[RTW_MAX_SUBPOOLS], ring_ev[RTW_MAX_SUBPOOLS][2];
       cudaGraph_t graph[RTW_MAX_SUBPOOLS];
       cudaGraphExec_t exec[RTW_MAX_SUBPOOLS];
@@ -536,8 +542,8 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
         launches++;
         RTW_CUDA_TRY(cudaStreamBeginCapture(sk, cudaStreamCaptureModeThreadLocal));
         for (int b = 0; b < BATCH; ++b) {
-          k_wave_traverse<false><<<wh->blocks_traverse, 128, 0, sk>>>(s->dev, wk[k], (uint32_t)(b & 1));
-          k_wave_shade<<<wh->blocks_shade, 128, 0, sk>>>(s->dev, f, wk[k], d_accum, (uint32_t)(b & 1));
+          k_wave_traverse<false><<<grid_t, 128, 0, sk>>>(s->dev, wk[k], (uint32_t)(b & 1));
+          k_wave_shade<<<grid_s, 128, 0, sk>>>(s->dev, f, wk[k], d_accum, (uint32_t)(b & 1));
         }
         RTW_CUDA_TRY(cudaStreamEndCapture(sk, &graph[k]));
         RTW_CUDA_TRY(cudaGraphInstantiate(&exec[k], graph[k], 0));
