@@ -172,6 +172,16 @@ int rtw_pop_transform(rtw_scene *s);
 int rtw_begin_group(rtw_scene *s);
 int rtw_end_group(rtw_scene *s);
 
+/* ---- participating media: hittable/volumes.rs ----------------------------------------------- */
+/* ConstantMedium::new(boundary, density, texture) (volumes.rs:24-35): everything emitted until the
+ * matching rtw_end_medium is the BOUNDARY — exactly one sphere or cuboid, optionally inside
+ * push/pop transforms (the two shapes the reference's scenes use; anything else is
+ * RTW_ERR_UNSUPPORTED).  The medium is ONE canonical primitive (returned id); its boundary gets no
+ * ids.  Its material is Isotropic{texture} (material.rs:149-168).  The random draw of
+ * ConstantMedium::hit (volumes.rs:58) is keyed by (pixel, sample, bounce, medium id) — see DESIGN.md. */
+int rtw_begin_medium(rtw_scene *s, float density, int texture);
+int rtw_end_medium(rtw_scene *s);
+
 /* ---- primitives (return the canonical id of the first primitive they emit) ---------------- */
 int rtw_add_sphere(rtw_scene *s, const float center[3], float radius, int material); /* spherical.rs:80-105 */
 int rtw_add_moving_sphere(rtw_scene *s, const float center0[3], float time0, const float center1[3],
@@ -194,7 +204,8 @@ int rtw_scene_num_prims(const rtw_scene *s);
 int rtw_scene_num_nodes(const rtw_scene *s);
 int rtw_scene_num_instances(const rtw_scene *s); /* transform chains incl. the identity (index 0) */
 /* Host-side view of the flattening (works before rtw_build and without a GPU):
- * type (0 sphere, 1 moving sphere, 2 yz-rect, 3 xz-rect, 4 xy-rect, 5 triangle), instance chain
+ * type (0 sphere, 1 moving sphere, 2 yz-rect, 3 xz-rect, 4 xy-rect, 5 triangle, 6 sphere medium,
+ * 7 cuboid medium), instance chain
  * index and material of a primitive; and the wrappers of a chain, outermost first
  * (kind 0 = Translation{a,b,c = offset}, kind 1 = YRotation{a = sin, b = cos}); returns the op count. */
 int rtw_scene_prim_info(const rtw_scene *s, int prim_id, int32_t *type, int32_t *instance, int32_t *material);

@@ -37,6 +37,8 @@ typedef struct rtw_sink {
   int (*pop_transform)(void *s);
   int (*begin_group)(void *s);
   int (*end_group)(void *s);
+  int (*begin_medium)(void *s, float density, int texture);
+  int (*end_medium)(void *s);
   int (*add_sphere)(void *s, const float c[3], float radius, int material);
   int (*add_moving_sphere)(void *s, const float c0[3], float t0, const float c1[3], float t1, float radius, int material);
   int (*add_xy_rect)(void *s, float x0, float x1, float y0, float y1, float k, int material);

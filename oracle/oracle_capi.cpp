@@ -28,7 +28,7 @@ int fail(int code, const std::string& msg) {
 }
 
 // ---- scene description: recorded by the emit calls, instantiated twice by orc_build ----------
-enum DescKind { D_ROOT, D_GROUP, D_TRANSLATE, D_ROTY, D_SPHERE, D_MSPHERE, D_RECT, D_CUBOID, D_TRIS };
+enum DescKind { D_ROOT, D_GROUP, D_TRANSLATE, D_ROTY, D_SPHERE, D_MSPHERE, D_RECT, D_CUBOID, D_TRIS, D_MEDIUM };
 struct Desc {
   DescKind kind;
   float f[12] = {0};
@@ -159,6 +159,15 @@ void instantiate(orc_scene* s, const Desc& d, bool use_bvh, Rng& build_rng, std:
       c->sides.objects.push_back(make_rect(s, 0, p0[1], p1[1], p0[2], p1[2], p1[0], d.material, id + 4));
       c->sides.objects.push_back(make_rect(s, 0, p0[1], p1[1], p0[2], p1[2], p0[0], d.material, id + 5));
       out.push_back(HittablePtr(c.release()));
+      break;
+    }
+    case D_MEDIUM: {  // ConstantMedium::new(boundary, density, texture) (volumes.rs:24-35)
+      std::unique_ptr<ConstantMedium> m(new ConstantMedium());
+      m->boundary = wrap_children(s, d, use_bvh, build_rng);
+      m->neg_inv_density = -1.0f / d.f[0];
+      m->phase_function = std::static_pointer_cast<Isotropic>(s->materials[d.material]);
+      m->prim_id = d.first_prim;
+      out.push_back(HittablePtr(m.release()));
       break;
     }
     case D_TRIS: {
@@ -396,12 +405,46 @@ int orc_end_group(orc_scene* s) {
   return RTW_OK;
 }
 
+// true while the boundary of a medium is being emitted: its primitives get no canonical id
+static bool in_medium(orc_scene* s) {
+  for (Desc* d : s->stack)
+    if (d->kind == D_MEDIUM) return true;
+  return false;
+}
+
+int orc_begin_medium(orc_scene* s, float density, int texture) {
+  CHECK_SCENE(s);
+  if (!valid_tex(s, texture)) return fail(RTW_ERR_INVALID, "medium: bad texture id");
+  if (in_medium(s)) return fail(RTW_ERR_UNSUPPORTED, "medium: nested media are not supported");
+  for (Desc* d : s->stack)
+    if (d->kind == D_TRANSLATE || d->kind == D_ROTY) return fail(RTW_ERR_UNSUPPORTED, "medium: a transformed medium is not supported (transform the boundary)");
+  auto iso = std::make_shared<Isotropic>(s->textures[texture]);
+  iso->id = (int)s->materials.size();
+  s->materials.push_back(iso);
+  Desc* d = push_child(s, D_MEDIUM);
+  d->f[0] = density;
+  d->material = iso->id;
+  d->first_prim = s->num_prims;
+  s->num_prims += 1;
+  s->stack.push_back(d);
+  return d->first_prim;
+}
+int orc_end_medium(orc_scene* s) {
+  CHECK_SCENE(s);
+  Desc* top = s->stack.back();
+  if (top->kind != D_MEDIUM) return fail(RTW_ERR_STATE, "end_medium: no open medium");
+  if (top->children.size() != 1) return fail(RTW_ERR_INVALID, "end_medium: a medium needs exactly one boundary object");
+  s->stack.pop_back();
+  return RTW_OK;
+}
+
 int orc_add_sphere(orc_scene* s, const float c[3], float radius, int material) {
   CHECK_SCENE(s);
   if (!c || !valid_mat(s, material)) return fail(RTW_ERR_INVALID, "sphere: bad argument");
   Desc* d = push_child(s, D_SPHERE);
   d->f[0] = c[0]; d->f[1] = c[1]; d->f[2] = c[2]; d->f[3] = radius;
   d->material = material;
+  if (in_medium(s)) { d->first_prim = -1; return s->num_prims - 1; }
   d->first_prim = s->num_prims;
   s->num_prims += 1;
   return d->first_prim;
@@ -439,6 +482,7 @@ int orc_add_cuboid(orc_scene* s, const float p0[3], const float p1[3], int mater
   Desc* d = push_child(s, D_CUBOID);
   for (int a = 0; a < 3; ++a) { d->f[a] = p0[a]; d->f[3 + a] = p1[a]; }
   d->material = material;
+  if (in_medium(s)) { d->first_prim = -7; return s->num_prims - 1; }
   d->first_prim = s->num_prims;
   s->num_prims += 6;
   return d->first_prim;

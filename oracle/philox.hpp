@@ -60,6 +60,15 @@ struct Rng {
     ++draws;
     return buf[idx++];
   }
+  // A draw that does not advance the sequential stream: word 0 of the block (id, 0x80000000 | stage).
+  // Used where the reference draws INSIDE hit() (ConstantMedium, volumes.rs:58): the BVH backend tests
+  // objects in another order than the reference's list, so those draws are keyed by the object instead
+  // of by their position in the stream.
+  float gen_f32_keyed(uint32_t id) const {
+    uint32_t c[4] = {id, 0x80000000u | ctr[1], ctr[2], ctr[3]}, out[4];
+    philox4x32_10(c, key, out);
+    return (float)(out[0] >> 8) * (1.0f / 16777216.0f);
+  }
   // rand `Standard` for f32: 24 random bits, [0,1)
   float gen_f32() { return (float)(next_u32() >> 8) * (1.0f / 16777216.0f); }
   // rand `Standard` for f64: 53 random bits from a u64 (low word drawn first)

@@ -380,6 +380,16 @@ struct Dielectric : Material {  // material.rs:102-147
   }
 };
 
+struct Isotropic : Material {  // material.rs:149-168
+  TexturePtr albedo;
+  explicit Isotropic(TexturePtr a) : albedo(a) {}
+  bool scatter(const Ray& r_in, const HitRecord& rec, Rng& rng, Scatter& out) const override {
+    out.attenuation = albedo->value(rec.texture_uv, rec.p);
+    out.scattered_ray = Ray(rec.p, random_in_unit_sphere(rng), r_in.time);
+    return true;
+  }
+};
+
 struct DiffuseLight : Material {  // light_source.rs:13-24
   TexturePtr emit;
   explicit DiffuseLight(TexturePtr e) : emit(e) {}
@@ -699,6 +709,41 @@ struct YRotation : Hittable {  // transformations.rs:50-153
     out = bbox;
     return true;
   }
+};
+
+// ---------------------------------------------------------------------------------------------
+// hittable/volumes.rs
+// ---------------------------------------------------------------------------------------------
+struct ConstantMedium : Hittable {  // volumes.rs:18-83
+  HittablePtr boundary;
+  std::shared_ptr<Isotropic> phase_function;
+  float neg_inv_density;
+  int32_t prim_id;
+  // volumes.rs:38-78.  The one draw (volumes.rs:58) is keyed by prim_id (see philox.hpp).
+  bool hit(const Ray& r, float t_min, float t_max, Rng& rng, HitRecord& rec) const override {
+    const float INF = std::numeric_limits<float>::infinity();
+    HitRecord rec1, rec2;
+    if (!boundary->hit(r, -INF, INF, rng, rec1)) return false;
+    if (!boundary->hit(r, rec1.t + 0.0001f, INF, rng, rec2)) return false;
+    float rec1_t = rmax(rec1.t, t_min);
+    float rec2_t = rmin(rec2.t, t_max);
+    if (rec1_t >= rec2_t) return false;
+    rec1_t = rmax(rec1_t, 0.0f);
+    float ray_length = r.direction.length();
+    float distance_inside_boundary = (rec2_t - rec1_t) * ray_length;
+    float hit_distance = neg_inv_density * std::log10(rng.gen_f32_keyed((uint32_t)prim_id));  // [QUIRK] log10, not ln
+    if (hit_distance > distance_inside_boundary) return false;
+    float t = rec1_t + hit_distance / ray_length;
+    rec.p = r.at(t);
+    rec.normal = Vec3(1.0f, 0.0f, 0.0f);  // arbitrary
+    rec.material = phase_function.get();
+    rec.t = t;
+    rec.texture_uv = Point2d{0.0f, 0.0f};
+    rec.is_front_face = true;
+    rec.prim_id = prim_id;
+    return true;
+  }
+  bool bounding_box(float t0, float t1, Aabb& out) const override { return boundary->bounding_box(t0, t1, out); }
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -75,7 +75,7 @@ class BuildStats(C.Structure):
 _SINK_FUNCS = ["last_error", "scene_create", "scene_destroy", "add_texture_solid", "add_texture_checker",
                "add_texture_noise", "add_texture_uvdebug", "add_texture_image", "add_material_lambertian",
                "add_material_metal", "add_material_dielectric", "add_material_diffuse_light", "push_translation",
-               "push_rotation_y", "pop_transform", "begin_group", "end_group", "add_sphere", "add_moving_sphere",
+               "push_rotation_y", "pop_transform", "begin_group", "end_group", "begin_medium", "end_medium", "add_sphere", "add_moving_sphere",
                "add_xy_rect", "add_xz_rect", "add_yz_rect", "add_cuboid", "add_triangles", "build", "render"]
 
 
@@ -126,6 +126,8 @@ class Backend:
         f("pop_transform").argtypes = [C.c_void_p]
         f("begin_group").argtypes = [C.c_void_p]
         f("end_group").argtypes = [C.c_void_p]
+        f("begin_medium").argtypes = [C.c_void_p, C.c_float, C.c_int]
+        f("end_medium").argtypes = [C.c_void_p]
         f("add_sphere").argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_float, C.c_int]
         f("add_moving_sphere").argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_float, C.POINTER(C.c_float), C.c_float,
                                            C.c_float, C.c_int]
@@ -324,6 +326,8 @@ class Scene:
     def pop_transform(self): return self._c("pop_transform")
     def begin_group(self): return self._c("begin_group")
     def end_group(self): return self._c("end_group")
+    def begin_medium(self, density, tex): return self._c("begin_medium", density, tex)
+    def end_medium(self): return self._c("end_medium")
     def sphere(self, c, r, m): return self._c("add_sphere", _f3(c), r, m)
     def moving_sphere(self, c0, t0, c1, t1, r, m): return self._c("add_moving_sphere", _f3(c0), t0, _f3(c1), t1, r, m)
     def xy_rect(self, x0, x1, y0, y1, k, m): return self._c("add_xy_rect", x0, x1, y0, y1, k, m)

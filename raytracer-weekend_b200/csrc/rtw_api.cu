@@ -43,6 +43,12 @@ int current_instance(rtw_scene* s) {
 }
 
 int emit_prim(rtw_scene* s, uint32_t type, float4 g0, float4 g1, float4 g2, int material, int shade) {
+  if (s->medium_material >= 0) {  // inside rtw_begin_medium: only the boundary (sphere / cuboid) may come
+    if (type != PT_MEDIUM_SPHERE && type != PT_MEDIUM_BOX)
+      return set_error(RTW_ERR_UNSUPPORTED, "medium: the boundary must be one sphere or one cuboid");
+    if (s->medium_has_boundary) return set_error(RTW_ERR_INVALID, "medium: a medium needs exactly one boundary object");
+    s->medium_has_boundary = true;
+  }
   if (s->prim_meta.size() >= (size_t)0x0FFFFFFF) return set_error(RTW_ERR_UNSUPPORTED, "too many primitives");
   int inst = current_instance(s);
   int id = (int)s->prim_meta.size();
@@ -261,9 +267,38 @@ int rtw_end_group(rtw_scene* s) {
 }
 
 // ---- primitives ----------------------------------------------------------------------------------
+// ---- media ---------------------------------------------------------------------------------------
+int rtw_begin_medium(rtw_scene* s, float density, int texture) {
+  CHECK_OPEN(s);
+  if (!valid_tex(s, texture)) return set_error(RTW_ERR_INVALID, "medium: bad texture id");
+  if (s->medium_material >= 0) return set_error(RTW_ERR_UNSUPPORTED, "medium: nested media are not supported");
+  if (!s->open_ops.empty())
+    return set_error(RTW_ERR_UNSUPPORTED, "medium: a transformed medium is not supported (transform the boundary)");
+  MaterialRec m{};
+  m.type = MT_ISOTROPIC;  // Isotropic::new(texture) (volumes.rs:26, material.rs:149-152)
+  m.tex = texture;
+  s->materials.push_back(m);
+  s->medium_material = (int)s->materials.size() - 1;
+  s->medium_density = density;
+  s->medium_has_boundary = false;
+  s->medium_open_depth = s->open_kinds.size();
+  return (int)s->prim_meta.size();
+}
+int rtw_end_medium(rtw_scene* s) {
+  CHECK_OPEN(s);
+  if (s->medium_material < 0) return set_error(RTW_ERR_STATE, "end_medium: no open medium");
+  if (s->open_kinds.size() != s->medium_open_depth) return set_error(RTW_ERR_STATE, "end_medium: unbalanced push inside the medium");
+  if (!s->medium_has_boundary) return set_error(RTW_ERR_INVALID, "end_medium: a medium needs exactly one boundary object");
+  s->medium_material = -1;
+  return RTW_OK;
+}
+
 int rtw_add_sphere(rtw_scene* s, const float c[3], float radius, int material) {
   CHECK_OPEN(s);
   if (!c || !valid_mat(s, material)) return set_error(RTW_ERR_INVALID, "sphere: bad argument");
+  if (s->medium_material >= 0)  // boundary of a ConstantMedium: volumes.rs:24-35 (neg_inv_density = -1/density)
+    return emit_prim(s, PT_MEDIUM_SPHERE, make_float4(c[0], c[1], c[2], radius), make_float4(-1.0f / s->medium_density, 0, 0, 0),
+                     make_float4(0, 0, 0, 0), s->medium_material, -1);
   return emit_prim(s, PT_SPHERE, make_float4(c[0], c[1], c[2], radius), make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0),
                    material, -1);
 }
@@ -285,6 +320,9 @@ int rtw_add_yz_rect(rtw_scene* s, float y0, float y1, float z0, float z1, float 
 int rtw_add_cuboid(rtw_scene* s, const float p0[3], const float p1[3], int material) {
   CHECK_OPEN(s);
   if (!p0 || !p1 || !valid_mat(s, material)) return set_error(RTW_ERR_INVALID, "cuboid: bad argument");
+  if (s->medium_material >= 0)
+    return emit_prim(s, PT_MEDIUM_BOX, make_float4(p0[0], p0[1], p0[2], p1[0]),
+                     make_float4(p1[1], p1[2], -1.0f / s->medium_density, 0), make_float4(0, 0, 0, 0), s->medium_material, -1);
   // rectangular.rs:177-234: XY@z1, XY@z0, XZ@y1, XZ@y0, YZ@x1, YZ@x0
   int first = add_rect(s, PT_RECT_XY, p0[0], p1[0], p0[1], p1[1], p1[2], material);
   if (first < 0) return first;
@@ -347,7 +385,7 @@ int rtw_add_triangles(rtw_scene* s, uint32_t n, const float* vertices, const flo
 // ---- build / introspection ---------------------------------------------------------------------
 int rtw_build(rtw_scene* s, float time0, float time1, rtw_build_stats* stats) {
   CHECK_OPEN(s);
-  if (!s->open_kinds.empty()) return set_error(RTW_ERR_STATE, "build: unbalanced push/begin");
+  if (!s->open_kinds.empty() || s->medium_material >= 0) return set_error(RTW_ERR_STATE, "build: unbalanced push/begin");
   if (s->prim_meta.empty()) return set_error(RTW_ERR_INVALID, "build: empty scene");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);

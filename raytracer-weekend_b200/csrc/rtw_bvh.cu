@@ -107,6 +107,15 @@ __global__ void k_prim_setup(uint32_t n, const float4* __restrict__ raw, const u
       b.hi = mk(fmaxf(sc.x + rv.x, ec.x + rv.x), fmaxf(sc.y + rv.y, ec.y + rv.y), fmaxf(sc.z + rv.z, ec.z + rv.z));
       break;
     }
+    case PT_MEDIUM_SPHERE: {  // volumes.rs:80-82 -> spherical.rs:98-104 ; g1.x = -1/density
+      float r = fabsf(g0.w);
+      v3 c = mk(g0.x, g0.y, g0.z), rv = mk(r, r, r);
+      b.lo = c - rv; b.hi = c + rv;
+      break;
+    }
+    case PT_MEDIUM_BOX:  // volumes.rs:80-82 -> rectangular.rs:242-244 ; g0 = (p0, p1.x), g1 = (p1.yz, -1/density)
+      b.lo = mk(g0.x, g0.y, g0.z); b.hi = mk(g0.w, g1.x, g1.y);
+      break;
     case PT_RECT_YZ:  // rectangular.rs:161-166
       b.lo = mk(g1.x - 0.0001f, g0.x, g0.z); b.hi = mk(g1.x + 0.0001f, g0.y, g0.w);
       break;
@@ -516,6 +525,9 @@ int build_scene_device(rtw_scene* s, float time0, float time1, rtw_build_stats* 
   d.num_prims = n;
   d.num_nodes = n > 1 ? n - 1 : 1;
   d.has_instances = s->inst_range.size() > 1 ? 1u : 0u;
+  d.has_media = 0;
+  for (uint32_t m : s->prim_meta)
+    if ((m & 7u) >= PT_MEDIUM_SPHERE) { d.has_media = 1; break; }
   RTW_CUDA_TRY(cudaEventRecord(ev[1]));
 
   // ---- persistent outputs ---------------------------------------------------------------------

@@ -167,6 +167,12 @@ struct WaveIO {
   const WaveDev& w;
   const uint32_t* __restrict__ queue;
   uint32_t slot;
+  uint32_t seed_lo, seed_hi;
+  // key of the current path segment: (pixel, sample), stage = bounce + 1 — the stage the shade kernel uses
+  __device__ __forceinline__ void rng_key(Rng& rng) {
+    const uint4 st = w.state[slot];
+    rng.begin(((uint64_t)seed_hi << 32) | seed_lo, st.x, st.y, (st.w & 0xffu) + 1u);
+  }
   __device__ __forceinline__ bool load(uint32_t i, v3& o, v3& d, float& time, float& t_min, float& t_max) {
     slot = queue[i];
     const float4 o4 = w.ray_o[slot], d4 = w.ray_d[slot];
@@ -179,8 +185,9 @@ struct WaveIO {
   }
 };
 
-template <bool COUNT>
-__global__ void __launch_bounds__(128) k_wave_traverse(SceneDev sc, WaveDev w, uint32_t parity) {
+template <bool COUNT, bool MEDIA>
+__global__ void __launch_bounds__(128) k_wave_traverse(SceneDev sc, WaveDev w, uint32_t parity, uint32_t seed_lo,
+                                                       uint32_t seed_hi) {
   WaveCtl* ctl = w.ctl;
   const uint32_t count = ctl->count[parity];
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -190,8 +197,8 @@ __global__ void __launch_bounds__(128) k_wave_traverse(SceneDev sc, WaveDev w, u
   }
   const uint32_t lane = threadIdx.x & 31;
   TraverseCounters cnt;
-  WaveIO io{w, w.queue[parity], 0};
-  traverse_persistent<COUNT>(sc, io, count, &ctl->cursor_traverse, cnt);
+  WaveIO io{w, w.queue[parity], 0, seed_lo, seed_hi};
+  traverse_persistent<COUNT, MEDIA>(sc, io, count, &ctl->cursor_traverse, cnt);
   if (COUNT) {
     uint32_t p = cnt.pairs, q = cnt.prims, r = cnt.prim_bytes;
     for (int off = 16; off > 0; off >>= 1) {
@@ -449,9 +456,12 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
     RTW_CUDA_TRY(cudaStreamCreateWithFlags(&wh->stream, cudaStreamNonBlocking));
     for (auto& ps : wh->pool_stream) RTW_CUDA_TRY(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
     int nb = 0;
-    RTW_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wave_traverse<false>, 128, 0));
+    if (s->dev.has_media)
+      RTW_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wave_traverse<false, true>, 128, 0));
+    else
+      RTW_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wave_traverse<false, false>, 128, 0));
     wh->blocks_traverse = std::max(nb, 1) * s->num_sms;
-    RTW_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wave_traverse<true>, 128, 0));
+    RTW_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wave_traverse<true, true>, 128, 0));
     wh->blocks_traverse_count = std::max(nb, 1) * s->num_sms;
     RTW_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wave_shade, 128, 0));
     wh->blocks_shade = std::max(nb, 1) * s->num_sms;
@@ -542,7 +552,10 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
         launches++;
         RTW_CUDA_TRY(cudaStreamBeginCapture(sk, cudaStreamCaptureModeThreadLocal));
         for (int b = 0; b < BATCH; ++b) {
-          k_wave_traverse<false><<<grid_t, 128, 0, sk>>>(s->dev, wk[k], (uint32_t)(b & 1));
+          if (s->dev.has_media)
+            k_wave_traverse<false, true><<<grid_t, 128, 0, sk>>>(s->dev, wk[k], (uint32_t)(b & 1), f.seed_lo, f.seed_hi);
+          else
+            k_wave_traverse<false, false><<<grid_t, 128, 0, sk>>>(s->dev, wk[k], (uint32_t)(b & 1), f.seed_lo, f.seed_hi);
           k_wave_shade<<<grid_s, 128, 0, sk>>>(s->dev, f, wk[k], d_accum, (uint32_t)(b & 1));
         }
         RTW_CUDA_TRY(cudaStreamEndCapture(sk, &graph[k]));
@@ -594,9 +607,11 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
             RTW_CUDA_TRY(cudaEventRecord(e4[0], st));
           }
           if (count_trav)
-            k_wave_traverse<true><<<wh->blocks_traverse_count, 128, 0, st>>>(s->dev, wk[0], parity);
+            k_wave_traverse<true, true><<<wh->blocks_traverse_count, 128, 0, st>>>(s->dev, wk[0], parity, f.seed_lo, f.seed_hi);
+          else if (s->dev.has_media)
+            k_wave_traverse<false, true><<<wh->blocks_traverse_count, 128, 0, st>>>(s->dev, wk[0], parity, f.seed_lo, f.seed_hi);
           else
-            k_wave_traverse<false><<<wh->blocks_traverse, 128, 0, st>>>(s->dev, wk[0], parity);
+            k_wave_traverse<false, false><<<wh->blocks_traverse, 128, 0, st>>>(s->dev, wk[0], parity, f.seed_lo, f.seed_hi);
           if (time_kernels) {
             RTW_CUDA_TRY(cudaEventRecord(kev[kev.size() - 3], st));
             RTW_CUDA_TRY(cudaEventRecord(kev[kev.size() - 2], st));

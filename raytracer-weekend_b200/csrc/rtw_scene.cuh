@@ -38,6 +38,11 @@ struct rtw_scene {
   std::vector<rtw::InstOp> open_ops;
   std::vector<int> open_kinds;       // 0 transform, 1 group   (to validate pop / end order)
   std::vector<int> open_emitted;     // primitives emitted inside each open wrapper
+  // an open ConstantMedium: -1 none, else the Isotropic material id; its boundary has been emitted or not
+  int medium_material = -1;
+  float medium_density = 0.f;
+  bool medium_has_boundary = false;
+  size_t medium_open_depth = 0;      // open_kinds.size() at rtw_begin_medium
   int cur_inst = 0;                  // instance index of the current open chain
   bool cur_inst_valid = true;
   std::vector<uint2> inst_range;     // inst -> (first op, count) ; inst 0 = identity

@@ -40,6 +40,8 @@ struct BatchIO {
     time = rp[6]; t_min = rp[7]; t_max = rp[8];
     return true;
   }
+  // a bare ray batch has no pixel / sample: medium draws use the all-zero key (the oracle does the same)
+  __device__ __forceinline__ void rng_key(Rng& rng) { rng.begin(0, 0, 0, 0); }
   __device__ __forceinline__ void store(uint32_t i, v3 o, v3 d, float time, int32_t slot, float t, uint32_t meta) {
     int32_t id = slot >= 0 ? sc.slot_prim[slot] : -1;
     write_hit(sc, hits, i, o, d, time, id, sc.geom + 3 * (size_t)(slot >= 0 ? slot : 0), t, meta);
@@ -47,11 +49,12 @@ struct BatchIO {
 };
 
 // the product path: the same persistent traversal the wavefront renderer runs
+template <bool MEDIA>
 __global__ void __launch_bounds__(128) k_trace_bvh(SceneDev sc, const rtw_ray* __restrict__ rays, uint32_t n,
                                                    rtw_hit* __restrict__ hits, uint32_t* cursor) {
   BatchIO io{sc, rays, hits};
   TraverseCounters cnt;
-  traverse_persistent<false>(sc, io, n, cursor, cnt);
+  traverse_persistent<false, MEDIA>(sc, io, n, cursor, cnt);
 }
 
 __global__ void __launch_bounds__(128) k_trace_brute(SceneDev sc, const rtw_ray* __restrict__ rays, uint64_t n,
@@ -64,7 +67,9 @@ __global__ void __launch_bounds__(128) k_trace_brute(SceneDev sc, const rtw_ray*
   float best_t;
   uint32_t meta;
   int32_t id;
-  brute_closest(sc, o, d, time, t_min, t_max, id, best_t, meta);
+  Rng rng;
+  rng.begin(0, 0, 0, 0);
+  brute_closest(sc, o, d, time, t_min, t_max, rng, id, best_t, meta);
   write_hit(sc, hits, i, o, d, time, id, sc.raw_geom + 3 * (size_t)(id >= 0 ? id : 0), best_t, meta);
 }
 
@@ -77,7 +82,7 @@ int trace_closest_device(rtw_scene* s, const rtw_ray* d_rays, uint64_t n, rtw_hi
     // persistent grid; batches above 2^31 rays are split
     static thread_local int blocks_per_sm = 0;
     if (!blocks_per_sm) {
-      RTW_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_trace_bvh, (int)T, 0));
+      RTW_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_trace_bvh<true>, (int)T, 0));
       blocks_per_sm = blocks_per_sm > 0 ? blocks_per_sm : 1;
     }
     uint32_t* cursor = nullptr;
@@ -86,7 +91,10 @@ int trace_closest_device(rtw_scene* s, const rtw_ray* d_rays, uint64_t n, rtw_hi
       uint32_t chunk = (uint32_t)std::min<uint64_t>(n - done, 1ull << 30);
       RTW_CUDA_TRY(cudaMemsetAsync(cursor, 0, sizeof(uint32_t), st));
       uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)blocks_per_sm * s->num_sms, (chunk + T - 1) / T);
-      k_trace_bvh<<<grid, T, 0, st>>>(s->dev, d_rays + done, chunk, d_hits + done, cursor);
+      if (s->dev.has_media)
+        k_trace_bvh<true><<<grid, T, 0, st>>>(s->dev, d_rays + done, chunk, d_hits + done, cursor);
+      else
+        k_trace_bvh<false><<<grid, T, 0, st>>>(s->dev, d_rays + done, chunk, d_hits + done, cursor);
       done += chunk;
     }
     RTW_CUDA_TRY(cudaFreeAsync(cursor, st));

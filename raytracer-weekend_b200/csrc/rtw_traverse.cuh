@@ -57,7 +57,10 @@ struct TraverseCounters {
 // IO policy of traverse_persistent:
 //   bool load(uint32_t index, v3& o, v3& d, float& time, float& t_min, float& t_max)   fetch ray `index`
 //   void store(uint32_t index, v3 o, v3 d, float time, int32_t slot, float t, uint32_t meta)   publish its closest hit
-template <bool COUNT, class IO>
+//   void rng_key(Rng& rng)   (pixel, sample, stage, seed) of the current ray — only called when a medium is tested
+// MEDIA = the scene contains ConstantMedium primitives (compiled out otherwise: the keyed draw and the
+// boundary tests cost registers and branches in the hottest loop).
+template <bool COUNT, bool MEDIA, class IO>
 __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, uint32_t count, uint32_t* cursor,
                                                     TraverseCounters& cnt) {
   const uint32_t lane = threadIdx.x & 31;
@@ -154,12 +157,16 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
         }
         if (COUNT) {
           cnt.prims++;
-          cnt.prim_bytes += 4u + ((type == PT_SPHERE) ? 16u : ((type >= PT_RECT_YZ && type <= PT_RECT_XY) ? 32u : 48u));
+          cnt.prim_bytes += 4u + ((type == PT_SPHERE) ? 16u : (((type >= PT_RECT_YZ && type <= PT_RECT_XY) || type >= PT_MEDIUM_SPHERE) ? 32u : 48u));
         }
         const float4* __restrict__ g = sc.geom + 3 * (size_t)slot;
         float t;
         bool hit;
-        if (type >= PT_RECT_YZ && type <= PT_RECT_XY)
+        if (MEDIA && type >= PT_MEDIUM_SPHERE) {  // ConstantMedium: one keyed draw (volumes.rs:58)
+          Rng rng;
+          io.rng_key(rng);
+          hit = medium_t(type, g, oi, di, d, t_min, best_t, rng.gen_f32_keyed((uint32_t)__ldg(sc.slot_prim + slot)), t);
+        } else if (type >= PT_RECT_YZ && type <= PT_RECT_XY)
           hit = rect_t_perm(oA, oB, oK, dA, dB, dK, t_min, best_t, __ldg(g), __ldg(reinterpret_cast<const float*>(g + 1)), t);
         else
           hit = prim_t(type, g, oi, di, time, t_min, best_t, t);
@@ -190,7 +197,7 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
 // Every primitive in canonical order: hittable/mod.rs:57-69 literally (closest_so_far shrink,
 // later primitive wins on equal t).  The debug / ground-truth path of rtw_trace_closest.
 __device__ __forceinline__ void brute_closest(const SceneDev& sc, v3 o, v3 d, float time, float t_min, float t_max,
-                                              int32_t& best_id, float& best_t, uint32_t& best_meta) {
+                                              const Rng& rng, int32_t& best_id, float& best_t, uint32_t& best_meta) {
   best_id = -1;
   best_t = t_max;
   best_meta = 0;
@@ -205,7 +212,10 @@ __device__ __forceinline__ void brute_closest(const SceneDev& sc, v3 o, v3 d, fl
       cur_inst = inst;
     }
     float t;
-    if (prim_t(type, sc.raw_geom + 3 * (size_t)id, oi, di, time, t_min, best_t, t)) {
+    const float4* __restrict__ g = sc.raw_geom + 3 * (size_t)id;
+    const bool hit = (type >= PT_MEDIUM_SPHERE) ? medium_t(type, g, oi, di, d, t_min, best_t, rng.gen_f32_keyed(id), t)
+                                                : prim_t(type, g, oi, di, time, t_min, best_t, t);
+    if (hit) {
       best_t = t; best_id = (int32_t)id; best_meta = meta;
     }
   }

@@ -65,6 +65,8 @@ int rtwh_sink_open(const char* path, const char* prefix, int device, rtw_sink* o
   RTW_BIND(pop_transform, "pop_transform");
   RTW_BIND(begin_group, "begin_group");
   RTW_BIND(end_group, "end_group");
+  RTW_BIND(begin_medium, "begin_medium");
+  RTW_BIND(end_medium, "end_medium");
   RTW_BIND(add_sphere, "add_sphere");
   RTW_BIND(add_moving_sphere, "add_moving_sphere");
   RTW_BIND(add_xy_rect, "add_xy_rect");
@@ -275,6 +277,13 @@ void YRotation::flatten(Flattener& f) const {
   f.check(f.sink()->push_rotation_y(f.scene(), deg_), "push_rotation_y");
   inner_->flatten(f);
   f.check(f.sink()->pop_transform(f.scene()), "pop_transform");
+}
+
+void ConstantMedium::flatten(Flattener& f) const {
+  int t = tex_->flatten(f);
+  f.check(f.sink()->begin_medium(f.scene(), density_, t), "begin_medium");
+  boundary_->flatten(f);
+  f.check(f.sink()->end_medium(f.scene()), "end_medium");
 }
 
 void flatten_world(const HittableList& world, rtw_sink* sink, float time0, float time1, rtw_build_stats* stats) {

@@ -314,6 +314,16 @@ class YRotation : public Hittable {  // transformations.rs:50-153
   HittablePtr inner_;
   float deg_;
 };
+class ConstantMedium : public Hittable {  // volumes.rs:18-35 — ConstantMedium::new(boundary, density, texture)
+ public:
+  ConstantMedium(HittablePtr boundary, float density, TexturePtr texture) : boundary_(boundary), density_(density), tex_(texture) {}
+  void flatten(Flattener& f) const override;
+
+ private:
+  HittablePtr boundary_;
+  float density_;
+  TexturePtr tex_;
+};
 // Transformable sugar (transformations.rs:155-172)
 inline HittablePtr rotate_y(HittablePtr h, float deg) { return std::make_shared<YRotation>(h, deg); }
 inline HittablePtr translate(HittablePtr h, Vec3 off) { return std::make_shared<Translation>(h, off); }

@@ -131,6 +131,91 @@ World cornell_box(float aspect, HostRng&) {
   return w;
 }
 
+// scenes.rs:416-483
+World smokey_cornell_box(float aspect, HostRng&) {
+  World w;
+  auto red = Lambertian::new_solid_color(Color(0.65f, 0.05f, 0.05f));
+  auto white = Lambertian::new_solid_color(Color(0.73f, 0.73f, 0.73f));
+  auto green = Lambertian::new_solid_color(Color(0.12f, 0.45f, 0.15f));
+  auto light = std::make_shared<DiffuseLight>(SolidColor::new_rgb(7.0f, 7.0f, 7.0f));
+  HittablePtr box1 = translate(rotate_y(std::make_shared<Cuboid>(Point3(0.0f, 0.0f, 0.0f), Point3(165.0f, 330.0f, 165.0f), white), 15.0f),
+                               Vec3(265.0f, 0.0f, 295.0f));
+  HittablePtr box2 = translate(rotate_y(std::make_shared<Cuboid>(Point3(0.0f, 0.0f, 0.0f), Point3(165.0f, 165.0f, 165.0f), white), -18.0f),
+                               Vec3(130.0f, 0.0f, 65.0f));
+  box1 = std::make_shared<ConstantMedium>(box1, 0.005f, SolidColor::new_rgb(0.0f, 0.0f, 0.0f));
+  box2 = std::make_shared<ConstantMedium>(box2, 0.005f, SolidColor::new_rgb(1.0f, 1.0f, 1.0f));
+  w.objects.push_back(std::make_shared<YZRectangle>(0.0f, 555.0f, 0.0f, 555.0f, 555.0f, green));
+  w.objects.push_back(std::make_shared<YZRectangle>(0.0f, 555.0f, 0.0f, 555.0f, 0.0f, red));
+  w.objects.push_back(std::make_shared<XZRectangle>(113.0f, 443.0f, 127.0f, 432.0f, 554.0f, light));
+  w.objects.push_back(std::make_shared<XZRectangle>(0.0f, 555.0f, 0.0f, 555.0f, 0.0f, white));
+  w.objects.push_back(std::make_shared<XZRectangle>(0.0f, 555.0f, 0.0f, 555.0f, 555.0f, white));
+  w.objects.push_back(std::make_shared<XYRectangle>(0.0f, 555.0f, 0.0f, 555.0f, 555.0f, white));
+  w.objects.push_back(box1);
+  w.objects.push_back(box2);
+  w.cameras.push_back(make_cam(Point3(278.0f, 278.0f, -800.0f), Point3(278.0f, 278.0f, 0.0f), Vec3(0.0f, 1.0f, 0.0f), 40.0f, aspect, 0.0f, 10.0f));
+  w.background = Color(0.0f, 0.0f, 0.0f);
+  return w;
+}
+
+// scenes.rs:485-620
+World book2_final_scene(float aspect, HostRng& rng) {
+  World w;
+  HittableList boxes1;
+  auto ground = Lambertian::new_solid_color(Color(0.48f, 0.83f, 0.53f));
+  const int boxes_per_side = 20;
+  for (int ii = 0; ii < boxes_per_side; ++ii)
+    for (int jj = 0; jj < boxes_per_side; ++jj) {
+      float i = (float)ii, j = (float)jj;
+      float wd = 100.0f;
+      float x0 = -1000.0f + i * wd, z0 = -1000.0f + j * wd, y0 = 0.0f;
+      float x1 = x0 + wd, y1 = rng.gen_range(1.0f, 101.0f), z1 = z0 + wd;
+      boxes1.push_back(std::make_shared<Cuboid>(Point3(x0, y0, z0), Point3(x1, y1, z1), ground));
+    }
+  w.objects.push_back(std::make_shared<BvhNode>(boxes1, 0.0f, 1.0f));
+  w.objects.push_back(std::make_shared<XZRectangle>(123.0f, 423.0f, 147.0f, 412.0f, 554.0f,
+                                                    std::make_shared<DiffuseLight>(SolidColor::new_rgb(7.0f, 7.0f, 7.0f))));
+  Point3 center1(400.0f, 400.0f, 200.0f);
+  Point3 center2 = center1 + Vec3(30.0f, 0.0f, 0.0f);
+  w.objects.push_back(std::make_shared<MovingSphere>(center1, 0.0f, center2, 1.0f, 50.0f, Lambertian::new_solid_color(Color(0.7f, 0.3f, 0.1f))));
+  w.objects.push_back(std::make_shared<Sphere>(Point3(260.0f, 150.0f, 45.0f), 50.0f, std::make_shared<Dielectric>(1.5f)));
+  w.objects.push_back(std::make_shared<Sphere>(Point3(0.0f, 150.0f, 145.0f), 50.0f, std::make_shared<Metal>(Color(0.8f, 0.8f, 0.9f), 1.0f)));
+  auto boundary = std::make_shared<Sphere>(Point3(360.0f, 150.0f, 145.0f), 70.0f, std::make_shared<Dielectric>(1.5f));
+  w.objects.push_back(boundary);
+  w.objects.push_back(std::make_shared<ConstantMedium>(boundary, 0.2f, SolidColor::new_rgb(0.2f, 0.4f, 0.9f)));
+  auto fog = std::make_shared<Sphere>(Point3(0.0f, 0.0f, 0.0f), 5000.0f, std::make_shared<Dielectric>(1.5f));
+  w.objects.push_back(std::make_shared<ConstantMedium>(fog, 0.0001f, SolidColor::new_rgb(1.0f, 1.0f, 1.0f)));
+  w.objects.push_back(std::make_shared<Sphere>(Point3(400.0f, 200.0f, 400.0f), 100.0f,
+                                               std::make_shared<Lambertian>(ImageTexture::open("models/earthmap.jpg"))));
+  auto pertext = std::make_shared<Noise>(Perlin(rng), 0.1f);
+  w.objects.push_back(std::make_shared<Sphere>(Point3(220.0f, 280.0f, 300.0f), 80.0f, std::make_shared<Lambertian>(pertext)));
+  HittableList boxes2;
+  auto white = std::make_shared<Lambertian>(SolidColor::new_rgb(0.73f, 0.73f, 0.73f));
+  for (int k = 0; k < 1000; ++k) boxes2.push_back(std::make_shared<Sphere>(rng.random_min_max(0.0f, 165.0f), 10.0f, white));
+  w.objects.push_back(std::make_shared<Translation>(std::make_shared<YRotation>(std::make_shared<BvhNode>(boxes2, 0.0f, 1.0f), 15.0f),
+                                                    Vec3(-100.0f, 270.0f, 395.0f)));
+  Point3 look_from(478.0f, 278.0f, -600.0f), look_at(278.0f, 278.0f, 0.0f);
+  w.cameras.push_back(make_cam(look_from, look_at, Vec3(0.0f, 1.0f, 0.0f), 40.0f, aspect, 0.0f, (look_at - look_from).length()));
+  w.background = Color(0.0f, 0.0f, 0.0f);
+  return w;
+}
+
+// scenes.rs:622-667: 30 cameras around the Book-2 scene, the world wrapped in one BvhNode
+World animated_book2_final(float aspect, HostRng& rng) {
+  World base = book2_final_scene(aspect, rng);
+  World w;
+  Point3 look_at(278.0f, 278.0f, 278.0f);
+  const float len_s = 3.0f, fps = 10.0f;
+  const float frames = fps * len_s;
+  for (int frame = 0; frame < (int)frames; ++frame) {
+    float from_x = 478.0f - (float)frame * (2.0f * 478.0f) / frames;
+    Point3 look_from(from_x, 278.0f, -600.0f);
+    w.cameras.push_back(Camera(look_from, look_at, Vec3(0.0f, 1.0f, 0.0f), 40.0f, aspect, 1.0f, (look_at - look_from).length(), 0.0f, 1.0f));
+  }
+  w.objects.push_back(std::make_shared<BvhNode>(base.objects, 0.0f, 1.0f));
+  w.background = base.background;
+  return w;
+}
+
 // scenes.rs:669-717
 World simple_triangle(float aspect, HostRng&) {
   World w;
@@ -264,10 +349,6 @@ World stress(float aspect, HostRng& rng, size_t n_spheres, size_t n_shards) {
   return w;
 }
 
-[[noreturn]] void needs_volumes(const char* name) {
-  throw Error(std::string("scene '") + name + "' uses ConstantMedium / Isotropic (volumes.rs), which the cuda backend does not flatten yet");
-}
-
 }  // namespace
 
 std::vector<std::string> scene_names() {
@@ -310,7 +391,9 @@ World generate_scene(const std::string& full_name, float aspect_ratio, uint64_t 
   if (name == "stress") return stress(aspect_ratio, rng, args.size() > 0 ? args[0] : 1000000, args.size() > 1 ? args[1] : 1000000);
   if (name == "stress-spheres") return stress(aspect_ratio, rng, args.size() > 0 ? args[0] : 1000000, 0);
   if (name == "stress-triangles") return stress(aspect_ratio, rng, 0, args.size() > 0 ? args[0] : 1000000);
-  if (name == "smokey-cornell-box" || name == "book2-final-scene" || name == "animated-book2-final-scene") needs_volumes(name.c_str());
+  if (name == "smokey-cornell-box") return smokey_cornell_box(aspect_ratio, rng);
+  if (name == "book2-final-scene") return book2_final_scene(aspect_ratio, rng);
+  if (name == "animated-book2-final-scene") return animated_book2_final(aspect_ratio, rng);
   if (name == "wavefront-suspension-obj")
     throw Error("scene 'wavefront-suspension-obj': Normals_Try3.obj uses usemtl without mtllib; the reference panics on it "
                 "(triangular.rs:177-179)");

@@ -131,6 +131,35 @@ def test_emit_errors():
             s.trace_closest(rtw.make_rays([[0, 0, 0]], [[0, 0, 1]]))
 
 
+def test_medium_emit_rules():
+    b = rtw.cuda_backend()
+    with b.new_scene() as s:
+        white = s.texture_solid(1, 1, 1)
+        m = s.lambertian(white)
+        assert s.sphere((0, 0, 0), 1.0, m) == 0
+        assert s.begin_medium(0.01, white) == 1            # ConstantMedium = ONE canonical primitive ...
+        s.push_translation((1, 2, 3))
+        s.push_rotation_y(15.0)
+        s.cuboid((0, 0, 0), (1, 1, 1), m)                   # ... its boundary gets no ids
+        with pytest.raises(rtw.RtwError, match="exactly one boundary"):
+            s.sphere((0, 0, 0), 1.0, m)
+        s.pop_transform()
+        s.pop_transform()
+        s.end_medium()
+        assert s.num_prims == 2 and s.prim_info(1)[0] == 7 and s.prim_info(1)[1] == 1
+        assert s.begin_medium(0.2, white) == 2
+        with pytest.raises(rtw.RtwError, match="one sphere or one cuboid"):
+            s.xy_rect(0, 1, 0, 1, 0, m)
+        with pytest.raises(rtw.RtwError, match="exactly one boundary"):
+            s.end_medium()
+        s.sphere((5, 5, 5), 2.0, m)
+        s.end_medium()
+        assert s.prim_info(2)[0] == 6
+        s.push_translation((1, 0, 0))
+        with pytest.raises(rtw.RtwError, match="transformed medium"):
+            s.begin_medium(0.1, white)
+
+
 @pytest.mark.skipif(HAS_GPU, reason="checks the no-GPU failure mode")
 def test_no_gpu_fails_loudly_no_fallback():
     b = rtw.cuda_backend()

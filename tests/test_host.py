@@ -22,7 +22,7 @@ def test_scene_list_matches_the_reference_subcommands():
 @pytest.mark.parametrize("name,prims", [("cornell-box", 18), ("two-spheres", 2), ("two-perlin-spheres", 2), ("earth", 1),
                                         ("simple-light", 4), ("simple-triangle", 2), ("wavefront-cow-obj", 5806),
                                         ("cow-lambert-metal", 5806), ("monument-earth", 7800),
-                                        ("stress:300:20", 500)])
+                                        ("stress:300:20", 500), ("smokey-cornell-box", 8), ("book2-final-scene", 3409)])
 def test_scenes_flatten_into_a_sink(oracle, name, prims):
     with rtw.Scene.from_name(oracle, name, 16 / 9, seed=3) as s:
         assert s.num_prims == prims
@@ -44,15 +44,19 @@ def test_jumpy_balls_is_seeded_and_faithful(oracle):
 
 
 def test_unsupported_scenes_fail_with_a_reason(oracle):
-    for n in ("smokey-cornell-box", "book2-final-scene", "animated-book2-final-scene"):
-        with pytest.raises(rtw.RtwError, match="ConstantMedium"):
-            rtw.Scene.from_name(oracle, n, 1.0)
     with pytest.raises(rtw.RtwError, match="usemtl without mtllib"):
         rtw.Scene.from_name(oracle, "wavefront-suspension-obj", 1.0)
     with pytest.raises(rtw.RtwError, match="no decoded image"):   # the PNG is missing from the reference tree too (.MISSING_LARGE_BLOBS)
         rtw.Scene.from_name(oracle, "textured-monument", 1.0)
     with pytest.raises(rtw.RtwError, match="unknown scene"):
         rtw.Scene.from_name(oracle, "nope", 1.0)
+
+
+def test_animated_scene_has_thirty_cameras(oracle):
+    with rtw.Scene.from_name(oracle, "animated-book2-final-scene", 1.0, seed=1) as s:   # scenes.rs:622-667
+        assert len(s.cameras) == 30 and s.num_prims == 3409
+        assert s.cameras[0].origin[0] == 478.0 and s.cameras[0].lens_radius == 0.5
+        assert abs(s.cameras[29].origin[0] - (478.0 - 29 * 2 * 478.0 / 30)) < 1e-3
 
 
 def test_obj_loader_semantics(tmp_path):

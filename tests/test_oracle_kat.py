@@ -271,6 +271,66 @@ def test_yrotation_matches_manual_formula(oracle):
         assert h["t"] == t
 
 
+# ---- volumes -------------------------------------------------------------------------------------------------------
+def test_constant_medium_log10_quirk(oracle):
+    """volumes.rs:38-78: t = max(t1, t_min, 0) + (-1/density) * log10(xi) / |d|  — log10, not ln — accepted iff
+    it stays inside the boundary; normal (1,0,0), front face, uv (0,0).  xi = the medium's keyed Philox draw."""
+    def keyed_xi(prim_id, stage=0):
+        c = np.array([prim_id, 0x80000000 | stage, 0, 0], np.uint32)
+        k = np.zeros(2, np.uint32)
+        out = np.zeros(4, np.uint32)
+        oracle.fn("philox4x32_10")(c.ctypes.data, k.ctypes.data, out.ctypes.data)
+        return np.float32(out[0] >> 8) * np.float32(2.0 ** -24)
+
+    for density in (0.05, 0.5, 5.0):
+        with oracle.new_scene() as s:
+            white = s.texture_solid(1, 1, 1)
+            m = s.lambertian(white)
+            s.xy_rect(-20, 20, -20, 20, 50, m)           # id 0, far behind
+            assert s.begin_medium(density, white) == 1
+            s.sphere((0, 0, 0), 2.0, m)
+            s.end_medium()
+            assert s.begin_medium(density, white) == 2
+            s.push_translation((10, 0, 0))
+            s.cuboid((-1, -1, -1), (1, 1, 1), m)
+            s.pop_transform()
+            s.end_medium()
+            s.build()
+            for pid, o, chord in ((1, (0, 0, -5), 4.0), (2, (10, 0, -5), 2.0)):
+                d = np.array([0, 0, 2], np.float32)        # |d| = 2: t is in units of d
+                h = one_hit(s, o, d)
+                xi = keyed_xi(pid)
+                hd = np.float32(-1.0 / density) * np.log10(xi)
+                t_in = np.float32((5 - chord / 2) / 2)
+                if hd <= chord:
+                    assert h["prim_id"] == pid
+                    np.testing.assert_allclose(h["t"], t_in + hd / np.float32(2), rtol=2e-6)
+                    assert tuple(h["normal"]) == (1.0, 0.0, 0.0) and h["front_face"] == 1 and (h["u"], h["v"]) == (0.0, 0.0)
+                else:
+                    assert h["prim_id"] == 0                # passes through to the wall
+                # starting inside: the entry is clamped to t_min (volumes.rs:47-53)
+                h = one_hit(s, (o[0], o[1], 0.0), d)
+                if hd <= chord / 2:
+                    assert h["prim_id"] == pid
+                    np.testing.assert_allclose(h["t"], np.float32(0.001) + hd / np.float32(2), rtol=2e-5)
+
+
+def test_constant_medium_scatter_probability(oracle):
+    """P(scatter inside a chord L) = P(xi >= 10^(-density L)) = 1 - 10^(-density L): measure it with the renderer
+    (black medium in front of a white background: a scattered path is absorbed)."""
+    density, L = 0.3, 2.0
+    with oracle.new_scene() as s:
+        black = s.texture_solid(0, 0, 0)
+        assert s.begin_medium(density, black) == 0
+        s.cuboid((-50, -50, 0), (50, 50, L), s.lambertian(black))
+        s.end_medium()
+        s.build()
+        cam = rtw.camera_new((0, 0, -10), (0, 0, 0), (0, 1, 0), 1.0, 1.0)   # narrow view: chords ~ L
+        a, st = s.render(cam, s.params(64, 64, 16, seed=3, background=(1, 1, 1)))
+        transmitted = float(a.mean()) / 16
+        assert abs(transmitted - 10 ** (-density * L)) < 0.01, transmitted
+
+
 # ---- camera ------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("args", [
     ((13, 2, 3), (0, 0, 0), (0, 1, 0), 20.0, 16 / 9, 0.1, 10.0),
