@@ -65,6 +65,8 @@ struct FrameDev {
   unsigned long long pix_per_slice;  // owned tiles * tile_size^2 (includes out-of-image padding)
   unsigned long long n_items;
   uint32_t pool;
+  uint32_t fit32;       // n_items, nsamp * slices < 2^32: decode_item stays in 32-bit arithmetic
+  uint32_t tile_shift;  // log2(tile_size) when it is a power of two, else 0xffffffff
 };
 
 struct WaveHost {
@@ -85,21 +87,41 @@ struct Item {
 };
 
 __device__ __forceinline__ bool decode_item(const FrameDev& f, unsigned long long n, Item& it) {
-  uint32_t k = (uint32_t)(n / f.pix_per_slice);
-  unsigned long long q = n % f.pix_per_slice;
-  uint32_t tsq = f.tile_size * f.tile_size;
-  uint32_t tile_local = (uint32_t)(q / tsq), within = (uint32_t)(q % tsq);
-  unsigned long long tile = (unsigned long long)tile_local * f.part_count + f.part_rank;
+  uint32_t k, tile_local, within, tx, ty, wx, wy;
+  if (f.fit32) {  // warp-uniform; 64-bit divisions cost ~100 instructions each
+    const uint32_t n32 = (uint32_t)n, pps = (uint32_t)f.pix_per_slice;
+    k = n32 / pps;
+    const uint32_t q = n32 - k * pps;
+    if (f.tile_shift != 0xffffffffu) {
+      tile_local = q >> (2u * f.tile_shift);
+      within = q & ((1u << (2u * f.tile_shift)) - 1u);
+      wx = within & (f.tile_size - 1u);
+      wy = within >> f.tile_shift;
+    } else {
+      const uint32_t tsq = f.tile_size * f.tile_size;
+      tile_local = q / tsq; within = q - tile_local * tsq;
+      wy = within / f.tile_size; wx = within - wy * f.tile_size;
+    }
+    it.sample = f.sample_begin + (f.nsamp * k) / f.slices;
+    it.sample_end = f.sample_begin + (f.nsamp * (k + 1u)) / f.slices;
+  } else {
+    k = (uint32_t)(n / f.pix_per_slice);
+    const unsigned long long q = n % f.pix_per_slice;
+    const uint32_t tsq = f.tile_size * f.tile_size;
+    tile_local = (uint32_t)(q / tsq); within = (uint32_t)(q % tsq);
+    wy = within / f.tile_size; wx = within % f.tile_size;
+    it.sample = f.sample_begin + (uint32_t)(((unsigned long long)f.nsamp * k) / f.slices);
+    it.sample_end = f.sample_begin + (uint32_t)(((unsigned long long)f.nsamp * (k + 1)) / f.slices);
+  }
+  const unsigned long long tile = (unsigned long long)tile_local * f.part_count + f.part_rank;
   if (tile >= f.tiles_total) return false;
-  uint32_t tx = (uint32_t)(tile % f.tiles_x), ty = (uint32_t)(tile / f.tiles_x);
-  uint32_t x = tx * f.tile_size + within % f.tile_size;
-  uint32_t y_top = ty * f.tile_size + within / f.tile_size;
+  ty = (uint32_t)tile / f.tiles_x; tx = (uint32_t)tile - ty * f.tiles_x;
+  const uint32_t x = tx * f.tile_size + wx;
+  const uint32_t y_top = ty * f.tile_size + wy;
   if (x >= f.width || y_top >= f.height) return false;
-  uint32_t row = f.height - 1 - y_top;
+  const uint32_t row = f.height - 1 - y_top;
   it.pixel = row * f.width + x;
   it.slice = k;
-  it.sample = f.sample_begin + (uint32_t)(((unsigned long long)f.nsamp * k) / f.slices);
-  it.sample_end = f.sample_begin + (uint32_t)(((unsigned long long)f.nsamp * (k + 1)) / f.slices);
   return it.sample_end > it.sample;
 }
 
@@ -215,8 +237,55 @@ __global__ void __launch_bounds__(128) k_wave_traverse(SceneDev sc, WaveDev w, u
 }
 
 // ---- shade + scatter + regenerate -----------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_wave_shade(SceneDev sc, FrameDev f, WaveDev w, float* __restrict__ accum,
+// A warp shades 32 queue entries per trip.  Paths that end in a trip (15 % of the lanes on Cornell) are NOT
+// restarted in place: that ran the whole regeneration code (work-item decode, Philox, camera ray) with 2.3 of
+// 32 lanes active — a quarter of the kernel's issued instructions (profiles/r01f_shade_lines.txt).  They go
+// on a per-warp backlog in shared memory instead; once 32 are waiting the warp restarts them together.
+#define RTW_BACKLOG 64
+#define RTW_NEED_ITEM 0x80000000u
+
+struct ShadeBacklog {  // per warp; SoA so that lane i touches bank i
+  uint32_t slot[RTW_BACKLOG], pixel[RTW_BACKLOG], sample[RTW_BACKLOG], sample_end[RTW_BACKLOG], slice[RTW_BACKLOG];
+};
+
+// restart the paths of backlog entries [first, first + 32) (those with valid == true): lib.rs:83-86
+#ifdef RTW_NOINLINE_RARE
+static __device__ __noinline__ void regenerate(
+#else
+__device__ __forceinline__ void regenerate(
+#endif
+const FrameDev& f, const WaveDev& w, ShadeBacklog& bl, uint32_t idx, bool valid,
+                                           uint32_t* next_queue, uint32_t* next_count, uint32_t& new_paths) {
+  Item it;
+  uint32_t slot = 0;
+  bool need_item = false, go = false;
+  if (valid) {
+    slot = bl.slot[idx];
+    it.pixel = bl.pixel[idx]; it.sample = bl.sample[idx]; it.sample_end = bl.sample_end[idx]; it.slice = bl.slice[idx];
+    need_item = (it.slice & RTW_NEED_ITEM) != 0;
+    go = !need_item;
+  }
+  __syncwarp();
+  if (fetch_item(f, w.item_cursor, need_item, it)) {  // the slot finished its work item: pull the next one
+    w.sum[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+    go = true;
+  }
+  if (go) {
+    start_path(f, w, slot, it);
+    new_paths++;
+  }
+  queue_push(next_queue, next_count, go, slot);
+}
+
+#ifdef RTW_SHADE_MINBLOCKS  // A/B r01: 6 (80 registers) and 7 (72) are 4 % and 11 % slower than the default (94)
+__global__ void __launch_bounds__(128, RTW_SHADE_MINBLOCKS) k_wave_shade(
+#else
+__global__ void __launch_bounds__(128) k_wave_shade(
+#endif
+    SceneDev sc, FrameDev f, WaveDev w, float* __restrict__ accum,
                                                     uint32_t parity) {
+  __shared__ ShadeBacklog backlog[4];
+  ShadeBacklog& bl = backlog[threadIdx.x >> 5];
   WaveCtl* ctl = w.ctl;
   const uint32_t count = ctl->count[parity];
   const uint32_t* __restrict__ queue = w.queue[parity];
@@ -224,19 +293,25 @@ __global__ void __launch_bounds__(128) k_wave_shade(SceneDev sc, FrameDev f, Wav
   uint32_t* next_count = &ctl->count[parity ^ 1];
   if (blockIdx.x == 0 && threadIdx.x == 0) ctl->cursor_traverse = 0;  // for the next traversal launch
   const uint32_t lane = threadIdx.x & 31;
+  const uint32_t lane_lt = (1u << lane) - 1u;
   const uint64_t seed = ((uint64_t)f.seed_hi << 32) | f.seed_lo;
   uint32_t new_paths = 0;
+  uint32_t nback = 0;  // warp-uniform: entries waiting on the backlog
+  uint32_t grabbed = 0;
+  if (lane == 0) grabbed = atomicAdd(&ctl->cursor_shade, 32u);
   for (;;) {
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(&ctl->cursor_shade, 32u);
-    base = __shfl_sync(0xffffffffu, base, 0);
+    const uint32_t base = __shfl_sync(0xffffffffu, grabbed, 0);
     if (base >= count) break;
+#ifdef RTW_CURSOR_PREFETCH
+    if (lane == 0) grabbed = atomicAdd(&ctl->cursor_shade, 32u);
+#endif
     const uint32_t i = base + lane;
     const bool active = i < count;
     uint32_t slot = 0;
-    bool alive = false;       // slot continues into the next iteration
-    bool need_item = false;   // slot finished its item and wants another
+    bool alive = false;  // slot continues into the next iteration
+    bool ended = false;  // the path ended: restart the slot (next sample of its item, or a new item)
     Item it;
+    it.pixel = it.sample = it.sample_end = it.slice = 0;
     if (active) {
       slot = queue[i];
       const int2 h = w.hit[slot];
@@ -245,11 +320,10 @@ __global__ void __launch_bounds__(128) k_wave_shade(SceneDev sc, FrameDev f, Wav
       uint4 st = w.state[slot];
       v3 T = mk(T4.x, T4.y, T4.z);
       uint32_t bounce = st.w & 0xffu;
-      bool terminated;
       v3 L = mk(0.f, 0.f, 0.f);
       if (h.x < 0) {  // lib.rs:102-105: miss -> background
         L = T * f.background;
-        terminated = true;
+        ended = true;
       } else {
         const int32_t id = sc.slot_prim[h.x];
         const uint32_t meta = sc.prim_meta[id];
@@ -265,13 +339,13 @@ __global__ void __launch_bounds__(128) k_wave_shade(SceneDev sc, FrameDev f, Wav
         v3 att, out_dir;
         if (!material_scatter(sc, m, d, rec, rng, att, out_dir)) {  // lib.rs:111-114
           L = T * emitted;
-          terminated = true;
+          ended = true;
         } else {
           // L += T*emitted with emitted == 0 for every scattering material: exact no-op
           T = T * att;  // lib.rs:116
           bounce += 1;
-          terminated = bounce >= f.max_depth;  // lib.rs:98-100: depth exhausted -> black
-          if (!terminated) {
+          ended = bounce >= f.max_depth;  // lib.rs:98-100: depth exhausted -> black
+          if (!ended) {
             w.ray_o[slot] = make_float4(rec.p.x, rec.p.y, rec.p.z, o4.w);
             w.ray_d[slot] = make_float4(out_dir.x, out_dir.y, out_dir.z, 0.f);
             w.thr[slot] = make_float4(T.x, T.y, T.z, 0.f);
@@ -280,35 +354,46 @@ __global__ void __launch_bounds__(128) k_wave_shade(SceneDev sc, FrameDev f, Wav
           }
         }
       }
-      if (terminated) {
+      if (ended) {
         float4 s4 = w.sum[slot];
         v3 sum = mk(s4.x, s4.y, s4.z) + L;  // lib.rs:87: pixel_color += sample_ray(..)
+        it.pixel = st.x; it.sample = st.y + 1; it.sample_end = st.z; it.slice = st.w >> 8;
         if (st.y + 1 < st.z) {  // next sample of the same item
           w.sum[slot] = make_float4(sum.x, sum.y, sum.z, 0.f);
-          it.pixel = st.x; it.sample = st.y + 1; it.sample_end = st.z; it.slice = st.w >> 8;
-          start_path(f, w, slot, it);
-          new_paths++;
-          alive = true;
         } else {  // item done: publish the slice sum
-          uint32_t row = st.x / f.width, col = st.x % f.width;
+          uint32_t row = st.x / f.width, col = st.x - row * f.width;
           size_t pix = (size_t)(f.height - 1 - row) * f.width + col;
           if (f.slices == 1) {
             accum[3 * pix] = sum.x; accum[3 * pix + 1] = sum.y; accum[3 * pix + 2] = sum.z;
           } else {
             w.partial[(size_t)(st.w >> 8) * f.width * f.height + pix] = make_float4(sum.x, sum.y, sum.z, 0.f);
           }
-          need_item = true;
+          it.slice = RTW_NEED_ITEM;
         }
       }
     }
-    if (fetch_item(f, w.item_cursor, need_item, it)) {
-      w.sum[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
-      start_path(f, w, slot, it);
-      new_paths++;
-      alive = true;
-    }
     queue_push(next_queue, next_count, alive, slot);
+    const uint32_t m_end = __ballot_sync(0xffffffffu, ended);
+    if (ended) {
+      const uint32_t pos = nback + __popc(m_end & lane_lt);
+      bl.slot[pos] = slot; bl.pixel[pos] = it.pixel; bl.sample[pos] = it.sample; bl.sample_end[pos] = it.sample_end;
+      bl.slice[pos] = it.slice;
+    }
+    nback += __popc(m_end);
+    __syncwarp();
+#ifndef RTW_REGEN_THRESHOLD
+#define RTW_REGEN_THRESHOLD 32
+#endif
+#ifndef RTW_CURSOR_PREFETCH
+    if (lane == 0) grabbed = atomicAdd(&ctl->cursor_shade, 32u);
+#endif
+    if (nback >= RTW_REGEN_THRESHOLD) {
+      const uint32_t take = min(nback, 32u);
+      nback -= take;
+      regenerate(f, w, bl, nback + lane, lane < take, next_queue, next_count, new_paths);
+    }
   }
+  if (nback > 0) regenerate(f, w, bl, lane, lane < nback, next_queue, next_count, new_paths);
   for (int off = 16; off > 0; off >>= 1) new_paths += __shfl_xor_sync(0xffffffffu, new_paths, off);
   if (lane == 0 && new_paths) atomicAdd(&ctl->paths, (unsigned long long)new_paths);
 }
@@ -446,6 +531,12 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
   f.n_items = (nsamp == 0) ? 0ull : f.pix_per_slice * slices;
   pool = (uint32_t)std::min<unsigned long long>(pool, std::max<unsigned long long>((f.n_items + 31ull) & ~31ull, 32ull));
   f.pool = pool;
+  f.fit32 = (f.n_items < (1ull << 32) && (unsigned long long)nsamp * (slices + 1ull) < (1ull << 32)) ? 1u : 0u;
+  f.tile_shift = 0xffffffffu;
+  if ((f.tile_size & (f.tile_size - 1u)) == 0u) {
+    f.tile_shift = 0;
+    while ((1u << f.tile_shift) < f.tile_size) f.tile_shift++;
+  }
 
   // ---- scratch (kept on the scene between calls) -------------------------------------------------
   WaveHost* wh = (WaveHost*)s->wave;
