@@ -342,13 +342,15 @@ __global__ void k_karras(int n, const uint64_t* __restrict__ keys, uint32_t* __r
 
 // Kernel: leaves.  Slot s holds primitive vals[s]; copies its geometry and meta into slot order.
 __global__ void k_emit_leaves(uint32_t n, const uint32_t* __restrict__ vals, const float4* __restrict__ enc,
-                              const uint32_t* __restrict__ meta, float4* __restrict__ geom, int32_t* __restrict__ slot_prim,
-                              uint32_t* __restrict__ slot_meta) {
+                              const uint32_t* __restrict__ meta, const uint32_t* __restrict__ prim_mat,
+                              const int32_t* __restrict__ prim_shade, float4* __restrict__ geom,
+                              int32_t* __restrict__ slot_prim, uint32_t* __restrict__ slot_meta, int2* __restrict__ slot_ms) {
   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
   uint32_t id = vals[s];
   slot_prim[s] = (int32_t)id;
   slot_meta[s] = meta[id];
+  slot_ms[s] = make_int2((int)prim_mat[id], prim_shade[id]);
   geom[3 * (size_t)s] = enc[3 * (size_t)id];
   geom[3 * (size_t)s + 1] = enc[3 * (size_t)id + 1];
   geom[3 * (size_t)s + 2] = enc[3 * (size_t)id + 2];
@@ -518,7 +520,18 @@ int build_scene_device(rtw_scene* s, float time0, float time1, rtw_build_stats* 
   if ((rc = dev_upload(s, &d.tri_shade, s->tri_shade))) return rc;
   if ((rc = dev_upload(s, &d.inst_range, s->inst_range))) return rc;
   if ((rc = dev_upload(s, &d.inst_ops, s->inst_ops))) return rc;
-  if ((rc = dev_upload(s, &d.materials, s->materials))) return rc;
+  {  // SolidColor albedo / emit textures are copied into the material record (MaterialRec::solid)
+    std::vector<MaterialRec> mats = s->materials;
+    for (MaterialRec& m : mats) {
+      m.solid = 0;
+      if (m.type != MT_METAL && m.type != MT_DIELECTRIC && m.tex >= 0 && (size_t)m.tex < s->textures.size() &&
+          s->textures[m.tex].type == TT_SOLID) {
+        m.solid = 1;
+        m.r = s->textures[m.tex].f0; m.g = s->textures[m.tex].f1; m.b = s->textures[m.tex].f2;
+      }
+    }
+    if ((rc = dev_upload(s, &d.materials, mats))) return rc;
+  }
   if ((rc = dev_upload(s, &d.textures, s->textures))) return rc;
   if ((rc = dev_upload(s, &d.noise, s->noise_tables))) return rc;
   if ((rc = dev_upload(s, &d.texels, s->texels))) return rc;
@@ -534,7 +547,9 @@ int build_scene_device(rtw_scene* s, float time0, float time1, rtw_build_stats* 
   float4 *d_enc, *d_geom, *d_nodes;
   int32_t* d_slot_prim;
   uint32_t* d_slot_meta;
+  int2* d_slot_ms;
   if ((rc = dev_alloc(s, &d_slot_meta, n))) return rc;
+  if ((rc = dev_alloc(s, &d_slot_ms, n))) return rc;
   if ((rc = dev_alloc(s, &d_enc, 3 * (size_t)n))) return rc;
   if ((rc = dev_alloc(s, &d_geom, 3 * (size_t)n))) return rc;
   if ((rc = dev_alloc(s, &d_nodes, 4 * (size_t)d.num_nodes))) return rc;
@@ -614,7 +629,7 @@ int build_scene_device(rtw_scene* s, float time0, float time1, rtw_build_stats* 
   k_refit<<<G, T>>>(n, d_v0, d_lo, d_hi, rp, d_nparent, d_lparent, d_nrange, d_flags, d_heights, d_ncost, d_collapsed,
                     d_nodes, d_root, d_info);
   if (n > 1) k_sort_leaf_ranges<<<G, T>>>(n - 1, d_collapsed, d_nparent, d_nrange, d.prim_meta, d_v0);
-  k_emit_leaves<<<G, T>>>(n, d_v0, d_enc, d.prim_meta, d_geom, d_slot_prim, d_slot_meta);
+  k_emit_leaves<<<G, T>>>(n, d_v0, d_enc, d.prim_meta, d.prim_mat, d.prim_shade, d_geom, d_slot_prim, d_slot_meta, d_slot_ms);
   RTW_CUDA_TRY(cudaGetLastError());
   RTW_CUDA_TRY(cudaEventRecord(ev[2]));
   RTW_CUDA_TRY(cudaEventSynchronize(ev[2]));
@@ -629,6 +644,7 @@ int build_scene_device(rtw_scene* s, float time0, float time1, rtw_build_stats* 
   d.raw_geom = d_enc;
   d.slot_prim = d_slot_prim;
   d.slot_meta = d_slot_meta;
+  d.slot_ms = d_slot_ms;
 
   float ms_up = 0.f, ms_build = 0.f;
   cudaEventElapsedTime(&ms_up, ev[0], ev[1]);

@@ -10,9 +10,13 @@
 //   alone — the image is bit-reproducible for any pool size, GPU count or scheduling.
 // * sample_ray's recursion (lib.rs:97-117) is run in its iterative form L += T*e; T *= a
 //   (SURVEY.md §8 a3); one iteration of the wavefront = one path segment per live slot.
-// * Both kernels are persistent: grid = SMs x resident blocks, warps pull 32 queue entries at a
-//   time from a device-side cursor, so no launch parameter depends on the live count and the host
-//   only synchronises every few iterations to learn whether the queue is empty.
+// * Both kernels are persistent: grid = SMs x resident blocks, warps pull 32 entries at a time from
+//   a device-side cursor, so no launch parameter depends on the live count and the host only
+//   synchronises every few iterations to learn whether anything is left.
+// * While work items remain every slot is busy, so entry i of an iteration simply IS slot i
+//   ("identity" mode: coalesced state accesses, no queue, no compaction atomics).  Once the item
+//   cursor has run dry the shade kernel compacts the surviving slots into a queue each iteration
+//   ("queue" mode), so the tail of the frame costs time proportional to the live paths.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -34,10 +38,12 @@ struct WaveCtl {           // one per sub-pool (+ one extra whose item_cursor is
   unsigned long long pairs;
   unsigned long long prims;
   unsigned long long prim_bytes;
-  uint32_t count[2];
+  uint32_t count[2];       // entries of the iteration with that parity (identity mode: slot_count)
   uint32_t cursor_traverse;
   uint32_t cursor_shade;
-  uint32_t pad[2];
+  uint32_t qmode[2];       // 0 = identity (entry i is slot slot_base + i), 1 = queue[parity] lists the live slots
+  uint32_t exhausted;      // (shared ctl only) the item cursor ran past n_items
+  uint32_t pad[3];
 };
 
 struct WaveDev {
@@ -51,6 +57,7 @@ struct WaveDev {
   float4* partial;  // [slices][w*h] slice sums (slices > 1)
   WaveCtl* ctl;                      // this sub-pool's counters
   unsigned long long* item_cursor;   // shared by all sub-pools
+  uint32_t* exhausted;               // shared by all sub-pools
   uint32_t slot_base, slot_count;    // this sub-pool's slots: [slot_base, slot_base + slot_count)
 };
 
@@ -127,7 +134,8 @@ __device__ __forceinline__ bool decode_item(const FrameDev& f, unsigned long lon
 
 // Warp-cooperative fetch: every lane with `need` gets a valid item or learns that none are left.
 // Must be called by all 32 lanes.
-__device__ __forceinline__ bool fetch_item(const FrameDev& f, unsigned long long* item_cursor, bool need, Item& it) {
+__device__ __forceinline__ bool fetch_item(const FrameDev& f, const WaveDev& w, bool need, Item& it) {
+  unsigned long long* item_cursor = w.item_cursor;
   const uint32_t lane = threadIdx.x & 31;
   bool got = false;
   for (;;) {
@@ -136,7 +144,10 @@ __device__ __forceinline__ bool fetch_item(const FrameDev& f, unsigned long long
     unsigned long long base = 0;
     if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(item_cursor, (unsigned long long)__popc(m));
     base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-    if (base >= f.n_items) break;  // exhausted (cursor may overshoot; harmless)
+    if (base + __popc(m) > f.n_items) {  // ran dry (the cursor may overshoot; harmless): later iterations compact
+      if (lane == 0) *w.exhausted = 1u;
+      if (base >= f.n_items) break;
+    }
     if (need && !got) {
       unsigned long long n = base + __popc(m & ((1u << lane) - 1u));
       if (n < f.n_items) got = decode_item(f, n, it);
@@ -173,21 +184,26 @@ __device__ __forceinline__ void queue_push(uint32_t* queue, uint32_t* count, boo
 __global__ void k_wave_init(SceneDev sc, FrameDev f, WaveDev w) {
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;  // block = 128 threads: whole warps reach the ballots
   const uint32_t slot = w.slot_base + tid;
+  if (tid == 0) {  // iteration 0 reads the slots in identity mode
+    w.ctl->count[0] = w.slot_count;
+    w.ctl->qmode[0] = 0;
+  }
   Item it;
-  bool got = fetch_item(f, w.item_cursor, tid < w.slot_count, it);
+  bool got = fetch_item(f, w, tid < w.slot_count, it);
   if (got) {
     start_path(f, w, slot, it);
     w.sum[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+  } else if (tid < w.slot_count) {
+    w.ray_d[slot] = make_float4(0.f, 0.f, 0.f, 1.f);  // dead slot (ray_d.w != 0)
   }
   uint32_t m = __ballot_sync(0xffffffffu, got);
   if ((threadIdx.x & 31) == 0 && m) atomicAdd(&w.ctl->paths, (unsigned long long)__popc(m));
-  queue_push(w.queue[0], &w.ctl->count[0], got, slot);
 }
 
 // ---- traversal -----------------------------------------------------------------------------------
 struct WaveIO {
   const WaveDev& w;
-  const uint32_t* __restrict__ queue;
+  const uint32_t* __restrict__ queue;  // nullptr: identity mode
   uint32_t slot;
   uint32_t seed_lo, seed_hi;
   // key of the current path segment: (pixel, sample), stage = bounce + 1 — the stage the shade kernel uses
@@ -196,8 +212,9 @@ struct WaveIO {
     rng.begin(((uint64_t)seed_hi << 32) | seed_lo, st.x, st.y, (st.w & 0xffu) + 1u);
   }
   __device__ __forceinline__ bool load(uint32_t i, v3& o, v3& d, float& time, float& t_min, float& t_max) {
-    slot = queue[i];
+    slot = queue ? queue[i] : w.slot_base + i;
     const float4 o4 = w.ray_o[slot], d4 = w.ray_d[slot];
+    if (d4.w != 0.f) return false;  // dead slot (identity mode at the end of the frame)
     o = mk(o4.x, o4.y, o4.z); d = mk(d4.x, d4.y, d4.z); time = o4.w;
     t_min = 0.001f; t_max = __int_as_float(0x7f800000);  // lib.rs:102: world.hit(r, 0.001, f32::INFINITY)
     return true;
@@ -212,14 +229,18 @@ __global__ void __launch_bounds__(128) k_wave_traverse(SceneDev sc, WaveDev w, u
                                                        uint32_t seed_hi) {
   WaveCtl* ctl = w.ctl;
   const uint32_t count = ctl->count[parity];
+  const uint32_t in_queue = ctl->qmode[parity];
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    ctl->cursor_shade = 0;        // consumed by the shade kernel that follows
-    ctl->count[parity ^ 1] = 0;   // the queue that shade kernel fills (its old content was consumed last iteration)
-    ctl->segments += count;
+    ctl->cursor_shade = 0;  // consumed by the shade kernel that follows
+    // What the shade kernel that follows writes for the next iteration: a queue once the work items have run
+    // out (decided HERE, between launches, so that all of its blocks agree), else nothing (identity).
+    const uint32_t out_queue = (in_queue || *w.exhausted) ? 1u : 0u;
+    ctl->qmode[parity ^ 1] = out_queue;
+    ctl->count[parity ^ 1] = out_queue ? 0u : w.slot_count;
   }
   const uint32_t lane = threadIdx.x & 31;
   TraverseCounters cnt;
-  WaveIO io{w, w.queue[parity], 0, seed_lo, seed_hi};
+  WaveIO io{w, in_queue ? w.queue[parity] : nullptr, 0, seed_lo, seed_hi};
   traverse_persistent<COUNT, MEDIA>(sc, io, count, &ctl->cursor_traverse, cnt);
   if (COUNT) {
     uint32_t p = cnt.pairs, q = cnt.prims, r = cnt.prim_bytes;
@@ -255,7 +276,8 @@ static __device__ __noinline__ void regenerate(
 __device__ __forceinline__ void regenerate(
 #endif
 const FrameDev& f, const WaveDev& w, ShadeBacklog& bl, uint32_t idx, bool valid,
-                                           uint32_t* next_queue, uint32_t* next_count, uint32_t& new_paths) {
+                                           uint32_t* next_queue, uint32_t* next_count, bool out_queue,
+                                           uint32_t& new_paths) {
   Item it;
   uint32_t slot = 0;
   bool need_item = false, go = false;
@@ -266,15 +288,17 @@ const FrameDev& f, const WaveDev& w, ShadeBacklog& bl, uint32_t idx, bool valid,
     go = !need_item;
   }
   __syncwarp();
-  if (fetch_item(f, w.item_cursor, need_item, it)) {  // the slot finished its work item: pull the next one
+  if (fetch_item(f, w, need_item, it)) {  // the slot finished its work item: pull the next one
     w.sum[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
     go = true;
   }
   if (go) {
     start_path(f, w, slot, it);
     new_paths++;
+  } else if (valid) {
+    w.ray_d[slot] = make_float4(0.f, 0.f, 0.f, 1.f);  // no work left for this slot: dead (ray_d.w != 0)
   }
-  queue_push(next_queue, next_count, go, slot);
+  if (out_queue) queue_push(next_queue, next_count, go, slot);
 }
 
 #ifdef RTW_SHADE_MINBLOCKS  // A/B r01: 6 (80 registers) and 7 (72) are 4 % and 11 % slower than the default (94)
@@ -288,14 +312,15 @@ __global__ void __launch_bounds__(128) k_wave_shade(
   ShadeBacklog& bl = backlog[threadIdx.x >> 5];
   WaveCtl* ctl = w.ctl;
   const uint32_t count = ctl->count[parity];
-  const uint32_t* __restrict__ queue = w.queue[parity];
+  const uint32_t* __restrict__ queue = ctl->qmode[parity] ? w.queue[parity] : nullptr;  // nullptr: identity
+  const bool out_queue = ctl->qmode[parity ^ 1] != 0;
   uint32_t* next_queue = w.queue[parity ^ 1];
   uint32_t* next_count = &ctl->count[parity ^ 1];
   if (blockIdx.x == 0 && threadIdx.x == 0) ctl->cursor_traverse = 0;  // for the next traversal launch
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t lane_lt = (1u << lane) - 1u;
   const uint64_t seed = ((uint64_t)f.seed_hi << 32) | f.seed_lo;
-  uint32_t new_paths = 0;
+  uint32_t new_paths = 0, nseg = 0;
   uint32_t nback = 0;  // warp-uniform: entries waiting on the backlog
   uint32_t grabbed = 0;
   if (lane == 0) grabbed = atomicAdd(&ctl->cursor_shade, 32u);
@@ -306,18 +331,26 @@ __global__ void __launch_bounds__(128) k_wave_shade(
     if (lane == 0) grabbed = atomicAdd(&ctl->cursor_shade, 32u);
 #endif
     const uint32_t i = base + lane;
-    const bool active = i < count;
+    bool active = i < count;
     uint32_t slot = 0;
     bool alive = false;  // slot continues into the next iteration
     bool ended = false;  // the path ended: restart the slot (next sample of its item, or a new item)
     Item it;
     it.pixel = it.sample = it.sample_end = it.slice = 0;
+    float4 o4, d4, T4, s4;
+    int2 h;
+    uint4 st;
+    if (active) {  // every load of the slot's state is issued before the first use
+      slot = queue ? queue[i] : w.slot_base + i;
+      h = w.hit[slot];
+      o4 = w.ray_o[slot]; d4 = w.ray_d[slot];
+      T4 = w.thr[slot];
+      st = w.state[slot];
+      s4 = w.sum[slot];
+      active = d4.w == 0.f;  // else: dead slot (identity mode at the end of the frame)
+    }
     if (active) {
-      slot = queue[i];
-      const int2 h = w.hit[slot];
-      const float4 o4 = w.ray_o[slot], d4 = w.ray_d[slot];
-      const float4 T4 = w.thr[slot];
-      uint4 st = w.state[slot];
+      nseg++;
       v3 T = mk(T4.x, T4.y, T4.z);
       uint32_t bounce = st.w & 0xffu;
       v3 L = mk(0.f, 0.f, 0.f);
@@ -325,13 +358,13 @@ __global__ void __launch_bounds__(128) k_wave_shade(
         L = T * f.background;
         ended = true;
       } else {
-        const int32_t id = sc.slot_prim[h.x];
-        const uint32_t meta = sc.prim_meta[id];
-        const MaterialRec m = sc.materials[sc.prim_mat[id]];
+        const uint32_t meta = sc.slot_meta[h.x];
+        const int2 ms = sc.slot_ms[h.x];
+        const MaterialRec m = sc.materials[ms.x];
         const v3 o = mk(o4.x, o4.y, o4.z), d = mk(d4.x, d4.y, d4.z);
-        const bool need_uv = (m.type == MT_LAMBERTIAN || m.type == MT_DIFFUSE_LIGHT) && texture_needs_uv(sc, m.tex);
+        const bool need_uv = !m.solid && (m.type == MT_LAMBERTIAN || m.type == MT_DIFFUSE_LIGHT) && texture_needs_uv(sc, m.tex);
         HitRec rec;
-        finalize_hit(sc, meta & 7u, meta >> RTW_META_TYPE_BITS, sc.geom + 3 * (size_t)h.x, sc.prim_shade[id], o, d, o4.w,
+        finalize_hit(sc, meta & 7u, meta >> RTW_META_TYPE_BITS, sc.geom + 3 * (size_t)h.x, ms.y, o, d, o4.w,
                      __int_as_float(h.y), need_uv, rec);
         const v3 emitted = material_emitted(sc, m, rec);  // lib.rs:107-109
         Rng rng;
@@ -355,7 +388,6 @@ __global__ void __launch_bounds__(128) k_wave_shade(
         }
       }
       if (ended) {
-        float4 s4 = w.sum[slot];
         v3 sum = mk(s4.x, s4.y, s4.z) + L;  // lib.rs:87: pixel_color += sample_ray(..)
         it.pixel = st.x; it.sample = st.y + 1; it.sample_end = st.z; it.slice = st.w >> 8;
         if (st.y + 1 < st.z) {  // next sample of the same item
@@ -372,7 +404,7 @@ __global__ void __launch_bounds__(128) k_wave_shade(
         }
       }
     }
-    queue_push(next_queue, next_count, alive, slot);
+    if (out_queue) queue_push(next_queue, next_count, alive, slot);
     const uint32_t m_end = __ballot_sync(0xffffffffu, ended);
     if (ended) {
       const uint32_t pos = nback + __popc(m_end & lane_lt);
@@ -390,12 +422,16 @@ __global__ void __launch_bounds__(128) k_wave_shade(
     if (nback >= RTW_REGEN_THRESHOLD) {
       const uint32_t take = min(nback, 32u);
       nback -= take;
-      regenerate(f, w, bl, nback + lane, lane < take, next_queue, next_count, new_paths);
+      regenerate(f, w, bl, nback + lane, lane < take, next_queue, next_count, out_queue, new_paths);
     }
   }
-  if (nback > 0) regenerate(f, w, bl, lane, lane < nback, next_queue, next_count, new_paths);
-  for (int off = 16; off > 0; off >>= 1) new_paths += __shfl_xor_sync(0xffffffffu, new_paths, off);
+  if (nback > 0) regenerate(f, w, bl, lane, lane < nback, next_queue, next_count, out_queue, new_paths);
+  for (int off = 16; off > 0; off >>= 1) {
+    new_paths += __shfl_xor_sync(0xffffffffu, new_paths, off);
+    nseg += __shfl_xor_sync(0xffffffffu, nseg, off);
+  }
   if (lane == 0 && new_paths) atomicAdd(&ctl->paths, (unsigned long long)new_paths);
+  if (lane == 0 && nseg) atomicAdd(&ctl->segments, (unsigned long long)nseg);  // one world.hit per live entry (lib.rs:102)
 }
 
 // pixel_color = sum over slices, in slice order; pixels of other partitions = 0
@@ -608,6 +644,7 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
       wk[k] = w;
       wk[k].ctl = w.ctl + k;
       wk[k].item_cursor = &w.ctl[RTW_MAX_SUBPOOLS].item_cursor;
+      wk[k].exhausted = &w.ctl[RTW_MAX_SUBPOOLS].exhausted;
       wk[k].slot_base = base;
       wk[k].slot_count = (k + 1 == K) ? pool - base : std::min(per, pool - base);
       wk[k].queue[0] = w.queue[0] + base;
@@ -668,7 +705,7 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
           for (uint32_t k = 0; k < K; ++k) {
             if (!done[k]) {
               RTW_CUDA_TRY(cudaEventSynchronize(ring_ev[k][(i - 1) & 1]));
-              if (wh->pinned_ctl[2 * k + ((i - 1) & 1)].count[0] == 0) done[k] = true;  // absorbing: no live path, no item left
+              if (wh->pinned_ctl[2 * k + ((i - 1) & 1)].count[0] == 0) done[k] = true;  // absorbing: queue mode, no live path, no item left
             }
             all = all && done[k];
           }
