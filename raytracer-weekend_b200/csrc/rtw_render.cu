@@ -30,6 +30,9 @@ namespace rtw {
 namespace {
 
 #define RTW_MAX_SUBPOOLS 4
+// ray_d.w of a slot: 0 = a live ray, else
+#define RTW_SLOT_DEAD 1.0f     // no work left for the slot (end of the frame, identity mode)
+#define RTW_SLOT_PENDING 2.0f  // traversal suspended in the drain of the last launch (rtw_traverse.cuh)
 
 struct WaveCtl {           // one per sub-pool (+ one extra whose item_cursor is the shared work-item cursor)
   unsigned long long item_cursor;
@@ -194,7 +197,7 @@ __global__ void k_wave_init(SceneDev sc, FrameDev f, WaveDev w) {
     start_path(f, w, slot, it);
     w.sum[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
   } else if (tid < w.slot_count) {
-    w.ray_d[slot] = make_float4(0.f, 0.f, 0.f, 1.f);  // dead slot (ray_d.w != 0)
+    w.ray_d[slot] = make_float4(0.f, 0.f, 0.f, RTW_SLOT_DEAD);
   }
   uint32_t m = __ballot_sync(0xffffffffu, got);
   if ((threadIdx.x & 31) == 0 && m) atomicAdd(&w.ctl->paths, (unsigned long long)__popc(m));
@@ -211,21 +214,43 @@ struct WaveIO {
     const uint4 st = w.state[slot];
     rng.begin(((uint64_t)seed_hi << 32) | seed_lo, st.x, st.y, (st.w & 0xffu) + 1u);
   }
-  __device__ __forceinline__ bool load(uint32_t i, v3& o, v3& d, float& time, float& t_min, float& t_max) {
+#ifndef RTW_SUSPEND_LANES
+#define RTW_SUSPEND_LANES 0  // A/B r01 (cow, monument): 4 / 8 / 12 cost 3-12 % — the restarts outweigh the shorter drain
+#endif
+  static constexpr int kSuspendLanes = RTW_SUSPEND_LANES;
+  bool was_pending;
+  __device__ __forceinline__ bool load(uint32_t i, v3& o, v3& d, float& time, float& t_min, float& t_max, int32_t& slot0,
+                                       bool& resumed) {
     slot = queue ? queue[i] : w.slot_base + i;
     const float4 o4 = w.ray_o[slot], d4 = w.ray_d[slot];
-    if (d4.w != 0.f) return false;  // dead slot (identity mode at the end of the frame)
+    if (d4.w == RTW_SLOT_DEAD) return false;  // identity mode at the end of the frame
     o = mk(o4.x, o4.y, o4.z); d = mk(d4.x, d4.y, d4.z); time = o4.w;
     t_min = 0.001f; t_max = __int_as_float(0x7f800000);  // lib.rs:102: world.hit(r, 0.001, f32::INFINITY)
+    resumed = was_pending = d4.w == RTW_SLOT_PENDING;
+    if (resumed) {  // suspended by the previous launch with this hit
+      const int2 h = w.hit[slot];
+      slot0 = h.x; t_max = __int_as_float(h.y);
+    }
     return true;
   }
-  __device__ __forceinline__ void store(uint32_t, v3, v3, float, int32_t hslot, float t, uint32_t) {
+  __device__ __forceinline__ void store(uint32_t, v3, v3 d, float, int32_t hslot, float t, uint32_t) {
     w.hit[slot] = make_int2(hslot, __float_as_int(t));
+    if (was_pending) w.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.f);
+  }
+  __device__ __forceinline__ void suspend(uint32_t, int32_t hslot, float t) {
+    w.hit[slot] = make_int2(hslot, __float_as_int(t));
+    const float4 d4 = w.ray_d[slot];
+    w.ray_d[slot] = make_float4(d4.x, d4.y, d4.z, RTW_SLOT_PENDING);
   }
 };
 
 template <bool COUNT, bool MEDIA>
-__global__ void __launch_bounds__(128) k_wave_traverse(SceneDev sc, WaveDev w, uint32_t parity, uint32_t seed_lo,
+// 8 resident blocks (64 registers) for the product variant: A/B r01 +2..3 % over the compiler's own choice (72)
+#ifndef RTW_TRAVERSE_MINBLOCKS
+#define RTW_TRAVERSE_MINBLOCKS 8
+#endif
+__global__ void __launch_bounds__(128, (COUNT || MEDIA) ? 1 : RTW_TRAVERSE_MINBLOCKS) k_wave_traverse(
+    SceneDev sc, WaveDev w, uint32_t parity, uint32_t seed_lo,
                                                        uint32_t seed_hi) {
   WaveCtl* ctl = w.ctl;
   const uint32_t count = ctl->count[parity];
@@ -240,7 +265,7 @@ __global__ void __launch_bounds__(128) k_wave_traverse(SceneDev sc, WaveDev w, u
   }
   const uint32_t lane = threadIdx.x & 31;
   TraverseCounters cnt;
-  WaveIO io{w, in_queue ? w.queue[parity] : nullptr, 0, seed_lo, seed_hi};
+  WaveIO io{w, in_queue ? w.queue[parity] : nullptr, 0, seed_lo, seed_hi, false};
   traverse_persistent<COUNT, MEDIA>(sc, io, count, &ctl->cursor_traverse, cnt);
   if (COUNT) {
     uint32_t p = cnt.pairs, q = cnt.prims, r = cnt.prim_bytes;
@@ -296,7 +321,7 @@ const FrameDev& f, const WaveDev& w, ShadeBacklog& bl, uint32_t idx, bool valid,
     start_path(f, w, slot, it);
     new_paths++;
   } else if (valid) {
-    w.ray_d[slot] = make_float4(0.f, 0.f, 0.f, 1.f);  // no work left for this slot: dead (ray_d.w != 0)
+    w.ray_d[slot] = make_float4(0.f, 0.f, 0.f, RTW_SLOT_DEAD);  // no work left for this slot
   }
   if (out_queue) queue_push(next_queue, next_count, go, slot);
 }
@@ -347,7 +372,8 @@ __global__ void __launch_bounds__(128) k_wave_shade(
       T4 = w.thr[slot];
       st = w.state[slot];
       s4 = w.sum[slot];
-      active = d4.w == 0.f;  // else: dead slot (identity mode at the end of the frame)
+      alive = d4.w == RTW_SLOT_PENDING;  // traversal not finished: carried to the next iteration unshaded
+      active = d4.w == 0.f;              // RTW_SLOT_DEAD: identity mode at the end of the frame
     }
     if (active) {
       nseg++;
@@ -549,11 +575,11 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
   const uint32_t owned_tiles = f.tiles_total > f.part_rank ? (f.tiles_total - f.part_rank + f.part_count - 1) / f.part_count : 0;
   f.pix_per_slice = (unsigned long long)owned_tiles * f.tile_size * f.tile_size;
 
-  // Default pool (measured, profiles/r01_pool_sweep.txt): a flat scene (one converged primitive loop) peaks at
-  // 2^20 slots — its 88 B/slot state then stays L2-resident; a scene with a hierarchy amortises the fixed
-  // ramp/tail cost of the persistent kernels better with 2^21 (2^22 for frames above 4 Mpixel).
-  uint32_t pool = p->pool_size ? p->pool_size
-                               : ((s->dev.num_prims <= 32) ? (1u << 20) : (npix > (4u << 20) ? (1u << 22) : (1u << 21)));
+  // Default pool (measured, profiles/r01_sweeps.txt): every launch of the persistent traversal ends with a drain
+  // in which the SMs wait for the longest rays (~13 us flat scene, ~67 us cow), so launches should be few and
+  // large; the slot state is streamed coalesced (identity mode), it does not need to stay in L2.  2^22 slots
+  // for a flat scene, 2^23 with a hierarchy (104 B per slot: 0.4 / 0.9 GB).
+  uint32_t pool = p->pool_size ? p->pool_size : ((s->dev.num_prims <= 32) ? (1u << 22) : (1u << 23));
   pool = (pool + 31u) & ~31u;
   uint32_t slices = p->slices;
   if (slices == 0) {  // enough items that the last ones to finish are a small fraction of the frame
@@ -632,9 +658,10 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
   // counters and stream.  Their kernels depend only on their own predecessor, so the ramp-up and the
   // tail of one sub-pool's persistent kernel (~15 us per launch, measured by the pool-size sweep in
   // profiles/) overlap the body of another's, and latency-bound shading overlaps issue-bound traversal.
+  // (r01: K = 2 gained 4 % while every iteration compacted into queues; with identity slots and 2^22+ pools one
+  // pool is fastest — K = 1 / 2 / 3: cow 3507 / 3454 / 3347 Mrays/s, Cornell 7124 / 7113 / 6840.  Kept for experiments.)
   uint32_t K = 1;
   if (!count_trav && !time_kernels && pool >= (1u << 16)) {
-    K = 2;
     if (const char* e = getenv("RTW_SUBPOOLS")) K = (uint32_t)std::min(std::max(atoi(e), 1), RTW_MAX_SUBPOOLS);
   }
   WaveDev wk[RTW_MAX_SUBPOOLS];

@@ -34,7 +34,9 @@ struct BatchIO {
   const SceneDev& sc;
   const rtw_ray* __restrict__ rays;
   rtw_hit* __restrict__ hits;
-  __device__ __forceinline__ bool load(uint32_t i, v3& o, v3& d, float& time, float& t_min, float& t_max) {
+  static constexpr int kSuspendLanes = 0;  // a ray batch is answered in one launch
+  __device__ __forceinline__ void suspend(uint32_t, int32_t, float) {}
+  __device__ __forceinline__ bool load(uint32_t i, v3& o, v3& d, float& time, float& t_min, float& t_max, int32_t&, bool&) {
     const float* rp = reinterpret_cast<const float*>(rays + i);
     o = mk(rp[0], rp[1], rp[2]); d = mk(rp[3], rp[4], rp[5]);
     time = rp[6]; t_min = rp[7]; t_max = rp[8];

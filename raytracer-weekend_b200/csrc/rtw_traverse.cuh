@@ -20,6 +20,15 @@
 namespace rtw {
 
 #define RTW_LINK_DONE ((int32_t)0x80000000)  // ~slot never reaches it (slot < 2^28)
+#ifndef RTW_SPECULATE
+#define RTW_SPECULATE 0  // A/B r01 (profiles/r01_sweeps.txt): the vote alone wins; postponing costs 8 registers and wasted steps
+#endif
+#ifndef RTW_NODE_EXIT_LANES
+#define RTW_NODE_EXIT_LANES 8
+#endif
+#ifndef RTW_LEAF_PHASE_DRAIN
+#define RTW_LEAF_PHASE_DRAIN 0
+#endif
 #ifndef RTW_REFILL_IDLE
 #define RTW_REFILL_IDLE 8  // refill once this many lanes of the warp are idle
 #endif
@@ -54,8 +63,18 @@ struct TraverseCounters {
   uint32_t prim_bytes = 0;
 };
 
+// Drain cut-off (IO::kSuspendLanes > 0): once the cursor has run dry a warp only drains what it holds, and a
+// launch ends with every SM waiting for a handful of long rays (measured: 67 us of a 260 us launch on the cow
+// scene, profiles/r01_sweeps.txt).  A warp left with <= kSuspendLanes rays therefore SUSPENDS them: the closest
+// hit found so far is published with a "pending" mark, the next launch restarts the ray with that hit as its
+// t_max (the result of a closest-hit query does not depend on how it is split — same tie rule), and the shade
+// kernel leaves pending slots alone.  A restarted ray is never suspended again, so every ray finishes within
+// two launches.
+//
 // IO policy of traverse_persistent:
-//   bool load(uint32_t index, v3& o, v3& d, float& time, float& t_min, float& t_max)   fetch ray `index`
+//   bool load(uint32_t index, v3& o, v3& d, float& time, float& t_min, float& t_max, int32_t& slot0, bool& resumed)
+//        fetch ray `index`; slot0 >= 0 / resumed: the ray was suspended with the hit (slot0, t_max)
+//   void suspend(uint32_t index, int32_t slot, float t)   publish the closest hit so far, mark the ray pending
 //   void store(uint32_t index, v3 o, v3 d, float time, int32_t slot, float t, uint32_t meta)   publish its closest hit
 //   void rng_key(Rng& rng)   (pixel, sample, stage, seed) of the current ray — only called when a medium is tested
 // MEDIA = the scene contains ConstantMedium primitives (compiled out otherwise: the keyed draw and the
@@ -66,13 +85,14 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t lane_lt = (1u << lane) - 1u;
   bool active = false;
+  bool resumed = false;    // this ray was suspended by the previous launch: finish it
   bool exhausted = false;  // warp-uniform: the cursor ran past `count`
   // per-ray state
   uint32_t index = 0;
   v3 o = mk(0, 0, 0), d = mk(0, 0, 0), inv = mk(0, 0, 0), oi = o, di = d;
   float time = 0.f, t_min = 0.f, best_t = 0.f;
-  int32_t best_slot = -1, best_id = -2, link = RTW_LINK_DONE;
-  uint32_t best_meta = 0, meta = 0, cur_inst = 0, cur_pm = 0xffffffffu;
+  int32_t best_slot = -1, best_id = -2, link = RTW_LINK_DONE, pl_link = 0;
+  uint32_t best_meta = 0, meta = 0, pl_meta = 0, cur_inst = 0, cur_pm = 0xffffffffu;
   float oA = 0.f, oB = 0.f, oK = 0.f, dA = 0.f, dB = 0.f, dK = 0.f;  // ray permuted for the current rectangle run
   int2 stack[RTW_STACK_SIZE];
   int sp = 0;
@@ -89,22 +109,50 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
       if (!active) {
         index = base + __popc(idle & lane_lt);
         float t_max;
-        if (index < count && io.load(index, o, d, time, t_min, t_max)) {
+        int32_t slot0 = -1;
+        if (index < count && io.load(index, o, d, time, t_min, t_max, slot0, resumed)) {
           inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);  // aabb.rs:29
-          best_t = t_max; best_slot = -1; best_id = -2; best_meta = 0;
+          best_t = t_max; best_slot = slot0; best_id = -2;
+          best_meta = slot0 >= 0 ? __ldg(sc.slot_meta + slot0) : 0u;
           oi = o; di = d; cur_inst = 0; cur_pm = 0xffffffffu;
-          sp = 0; link = 0; meta = 0;
+          sp = 0; link = 0; meta = 0; pl_meta = 0;
           active = true;
         }
       }
     }
-    if (__ballot_sync(0xffffffffu, active) == 0) {
+    const uint32_t m_active = __ballot_sync(0xffffffffu, active);
+    if (m_active == 0) {
       if (exhausted) break;
       continue;
     }
-    // ---- (b) walk internal pairs until this lane holds a leaf (or runs dry) --------------------------
-    if (active) {
-      while (link >= 0) {
+    if (IO::kSuspendLanes > 0 && exhausted && __popc(m_active) <= IO::kSuspendLanes) {
+      if (active && !resumed) {
+        io.suspend(index, best_slot, best_t);
+        active = false;
+      }
+      if (__ballot_sync(0xffffffffu, active) == 0) break;
+    }
+    // ---- (b) node phase: walk internal pairs -----------------------------------------------------------
+    // Plain while-while keeps every lane that has reached a leaf waiting for the slowest one (measured on the
+    // cow scene: 8.3 of 32 lanes execute a node step, profiles/r01h).  Two remedies, after Aila & Laine:
+    //  * speculation: the first leaf a lane reaches is POSTPONED (pl_link / pl_meta) and the lane keeps walking
+    //    until it holds a second one; testing the postponed leaf later can only find hits the early test would
+    //    have found too (the closest hit does not depend on the order of the tests);
+    //  * the phase ends by vote: when no searching lane is empty-handed, or when fewer than
+    //    RTW_NODE_EXIT_LANES lanes would take another step while others have leaves waiting.
+    for (;;) {
+      const bool searching = active && link >= 0;
+      const uint32_t m_search = __ballot_sync(0xffffffffu, searching);
+      if (m_search == 0) break;
+#if RTW_SPECULATE
+      if (__ballot_sync(0xffffffffu, searching && pl_meta == 0u) == 0) break;
+#endif
+#if RTW_NODE_EXIT_LANES > 0
+      if (__popc(m_search) < RTW_NODE_EXIT_LANES &&
+          __any_sync(0xffffffffu, active && (pl_meta != 0u || (link < 0 && link != RTW_LINK_DONE))))
+        break;
+#endif
+      if (searching) {
         const float4* __restrict__ n = sc.nodes + 4 * (size_t)link;
         const float4 l0 = __ldg(n), l1 = __ldg(n + 1), r0 = __ldg(n + 2), r1 = __ldg(n + 3);
         if (COUNT) cnt.pairs++;
@@ -127,15 +175,39 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
         } else {
           link = RTW_LINK_DONE;
         }
+#if RTW_SPECULATE
+        if (link < 0 && link != RTW_LINK_DONE && pl_meta == 0u) {  // first leaf in hand: postpone it, keep walking
+          pl_link = link; pl_meta = meta;
+          if (sp > 0) {
+            const int2 e = stack[--sp];
+            link = e.x; meta = (uint32_t)e.y;
+          } else {
+            link = RTW_LINK_DONE;
+          }
+        }
+#endif
       }
     }
-    __syncwarp();
-    // ---- (c) test the primitives of the held leaf (a contiguous slot range) ---------------------------
+    // ---- (c) leaf phase: test the primitives of the held leaves (contiguous slot ranges) ---------------------
     // Inside a leaf the build sorted the slots by (instance, type): the ray is re-transformed /
     // re-permuted only when that key changes (cur_pm caches it).
-    if (active && link != RTW_LINK_DONE) {
-      const uint32_t first = (uint32_t)(~link);
-      const uint32_t nprim = meta;
+#if RTW_LEAF_PHASE_DRAIN
+    while (active && (pl_meta != 0u || (link < 0 && link != RTW_LINK_DONE))) {
+#else
+    for (int rep = 0; rep < 2 && active && (pl_meta != 0u || (link < 0 && link != RTW_LINK_DONE)); ++rep) {  // the postponed leaf, then the held one
+#endif
+      uint32_t first, nprim;
+      if (pl_meta != 0u) {
+        first = (uint32_t)(~pl_link); nprim = pl_meta; pl_meta = 0u;
+      } else {
+        first = (uint32_t)(~link); nprim = meta;
+        if (sp > 0) {
+          const int2 e = stack[--sp];
+          link = e.x; meta = (uint32_t)e.y;
+        } else {
+          link = RTW_LINK_DONE;
+        }
+      }
       for (uint32_t k = 0; k < nprim; ++k) {
         const uint32_t slot = first + k;
         const uint32_t pm = __ldg(sc.slot_meta + slot);
@@ -180,14 +252,9 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
           }
         }
       }
-      if (sp > 0) {
-        const int2 e = stack[--sp];
-        link = e.x; meta = (uint32_t)e.y;
-      } else {
-        link = RTW_LINK_DONE;
-      }
     }
-    if (active && link == RTW_LINK_DONE) {
+    __syncwarp();
+    if (active && link == RTW_LINK_DONE && pl_meta == 0u) {
       io.store(index, o, d, time, best_slot, best_t, best_meta);
       active = false;
     }

@@ -33,16 +33,16 @@ scene = rtw.Scene.from_name(gpu, scene_name, w / h, seed=2024, device=0)
 cam = scene.cameras[0]
 best = 0.0
 for i in range(5):
-    p = scene.params(w, h, spp, seed=2024)
+    p = scene.params(w, h, spp, seed=2024, pool_size=int(os.environ.get('AB_POOL', '0')))
     st = scene.render_device(cam, p, accum.data_ptr(), stream.cuda_stream)
     torch.cuda.synchronize()
     if i >= 2: best = max(best, st.segments / st.ms_render / 1e3)
-p = scene.params(w, h, spp, seed=2024, flags=2)
+p = scene.params(w, h, spp, seed=2024, flags=2, pool_size=int(os.environ.get('AB_POOL', '0')))
 for i in range(2):
     st = scene.render_device(cam, p, accum.data_ptr(), stream.cuda_stream)
 torch.cuda.synchronize()
-print('%%-10s %%-16s %%8.1f Mrays/s | single pool: traverse %%8.2f ms  shade %%8.2f ms  (%%d iterations, %%.1f Mseg)' %% (
-    %(var)r, %(work)r, best, st.ms_traverse, st.ms_shade, st.iterations, st.segments / 1e6))
+print('%%-10s %%-16s %%8.1f Mrays/s | single pool: traverse %%8.2f ms  shade %%8.2f ms  (%%d iterations, %%.1f Mseg, pool %%d)' %% (
+    %(var)r, %(work)r, best, st.ms_traverse, st.ms_shade, st.iterations, st.segments / 1e6, st.pool_size))
 """
 
 
