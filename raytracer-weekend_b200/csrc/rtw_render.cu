@@ -295,7 +295,7 @@ struct ShadeBacklog {  // per warp; SoA so that lane i touches bank i
 };
 
 // restart the paths of backlog entries [first, first + 32) (those with valid == true): lib.rs:83-86
-#ifdef RTW_NOINLINE_RARE
+#ifdef RTW_NOINLINE_REGEN
 static __device__ __noinline__ void regenerate(
 #else
 __device__ __forceinline__ void regenerate(

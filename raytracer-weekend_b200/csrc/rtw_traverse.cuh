@@ -30,7 +30,7 @@ namespace rtw {
 #define RTW_LEAF_PHASE_DRAIN 0
 #endif
 #ifndef RTW_REFILL_IDLE
-#define RTW_REFILL_IDLE 8  // refill once this many lanes of the warp are idle
+#define RTW_REFILL_IDLE 12  // refill once this many lanes of the warp are idle (A/B r01: 1 / 4 / 8 / 12 within 2 %, 12 best)
 #endif
 
 // Slab test of one child record against the ray: aabb.rs:23-48 with (a) the reciprocal hoisted out
@@ -56,6 +56,14 @@ __device__ __forceinline__ bool slab(float4 lo, float4 hi, v3 o, v3 inv, float t
   float t_far = __fmaf_rn(fabsf(t_max), 4.76837158e-7f, t_max);
   return t_min <= t_far;
 }
+
+#ifndef RTW_CURSOR_CHUNKS
+#define RTW_CURSOR_CHUNKS 0  // A/B r01: private 32-entry chunks with a prefetched cursor are 3-13 % SLOWER (partial refills, drain imbalance)
+#endif
+#ifndef RTW_PREFETCH_FAR
+#define RTW_PREFETCH_FAR 0
+#endif
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 struct TraverseCounters {
   uint32_t pairs = 0;
@@ -96,16 +104,47 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
   float oA = 0.f, oB = 0.f, oK = 0.f, dA = 0.f, dB = 0.f, dK = 0.f;  // ray permuted for the current rectangle run
   int2 stack[RTW_STACK_SIZE];
   int sp = 0;
+#if RTW_CURSOR_CHUNKS
+  uint32_t chunk_pos = 0, chunk_end = 0;  // warp-uniform: unused entries of the warp's current chunk
+  uint32_t next_base = 0;                 // lane 0: cursor value of the prefetched next chunk
+  if (lane == 0) next_base = atomicAdd(cursor, 32u);
+#endif
 
   for (;;) {
     // ---- (a) refill idle lanes -----------------------------------------------------------------
     const uint32_t idle = __ballot_sync(0xffffffffu, !active);
+#if RTW_CURSOR_CHUNKS
+    // The warp owns a chunk of 32 consecutive entries and has the NEXT chunk's cursor fetch already in flight
+    // (issued when the current chunk was opened): a refill never waits for an atomic round trip — 10.6 % of the
+    // kernel's stall samples on the flat Cornell scene, where all 32 lanes finish together (profiles/r01h).
+    uint32_t base = 0, take = 0;
+    if (idle != 0 && !exhausted && (__popc(idle) >= RTW_REFILL_IDLE || idle == 0xffffffffu)) {
+      if (chunk_pos == chunk_end) {  // open the prefetched chunk, prefetch the one after
+        chunk_pos = __shfl_sync(0xffffffffu, next_base, 0);
+        if (chunk_pos >= count) {
+          exhausted = true;
+          chunk_end = chunk_pos;
+        } else {
+          chunk_end = min(chunk_pos + 32u, count);
+          if (lane == 0) next_base = atomicAdd(cursor, 32u);
+        }
+      }
+      take = min((uint32_t)__popc(idle), chunk_end - chunk_pos);
+      base = chunk_pos;
+      chunk_pos += take;
+    }
+    if (take != 0) {
+      if (!active && (uint32_t)__popc(idle & lane_lt) >= take) {
+        // no entry left in this chunk for this lane: next trip
+      } else
+#else
     if (idle != 0 && !exhausted && (__popc(idle) >= RTW_REFILL_IDLE || idle == 0xffffffffu)) {
       const int leader = __ffs(idle) - 1;
       uint32_t base = 0;
       if ((int)lane == leader) base = atomicAdd(cursor, (uint32_t)__popc(idle));
       base = __shfl_sync(0xffffffffu, base, leader);
       if (base + __popc(idle) >= count) exhausted = true;
+#endif
       if (!active) {
         index = base + __popc(idle & lane_lt);
         float t_max;
@@ -161,8 +200,15 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
         const bool hr = slab(r0, r1, o, inv, t_min, best_t, tr);
         if (hl && hr) {
           const bool left_first = tl <= tr;
-          stack[sp++] = left_first ? make_int2(__float_as_int(r0.w), __float_as_int(r1.w))
-                                   : make_int2(__float_as_int(l0.w), __float_as_int(l1.w));
+          const int2 far = left_first ? make_int2(__float_as_int(r0.w), __float_as_int(r1.w))
+                                      : make_int2(__float_as_int(l0.w), __float_as_int(l1.w));
+          stack[sp++] = far;
+#if RTW_PREFETCH_FAR
+          // the postponed child is the likeliest later visit: start its 64-byte pair (or its first primitive)
+          // on the way to L2 now — only matters when the hierarchy does not fit the caches (config C5)
+          if (far.x >= 0) prefetch_l2(sc.nodes + 4 * (size_t)far.x);
+          else prefetch_l2(sc.geom + 3 * (size_t)(~far.x));
+#endif
           link = left_first ? __float_as_int(l0.w) : __float_as_int(r0.w);
           meta = left_first ? __float_as_uint(l1.w) : __float_as_uint(r1.w);
         } else if (hl) {
