@@ -138,19 +138,27 @@ def cpu_baseline(args, scene_name, w, h, max_depth=50):
         cam = so.cameras[0]
         accum = np.zeros((h, w, 3), np.float32)
 
-        def run(spp_begin, spp_end):
-            p = so.params(w, h, spp_end, seed=SEED, max_depth=max_depth, sample_begin=spp_begin, sample_end=spp_end)
+        def run(spp_begin, spp_end, part_count=1):
+            p = so.params(w, h, spp_end, seed=SEED, max_depth=max_depth, sample_begin=spp_begin, sample_end=spp_end,
+                          part_rank=0, part_count=part_count)
             st = rtw.RenderStats()
             t0 = time.perf_counter()
             orc.check(orc.fn("render_ex")(so.h, C.byref(cam), C.byref(p), accum.ctypes.data, C.byref(st), 2, 1, 0), "render_ex")
             return st.segments, time.perf_counter() - t0
 
-        seg, dt = run(0, 1)  # calibration: one sample per pixel
-        rate = seg / dt
-        spp = max(1, min(4096, int(args.cpu_seconds * rate / max(seg, 1))))
-        seg, dt = run(1, 1 + spp)
+        # calibration: one sample per pixel on every 64th 32x32 tile (interleaved over the frame)
+        seg, dt = run(0, 1, 64)
+        full_1spp = dt * 64.0
+        if full_1spp > args.cpu_seconds:  # a full-frame sample is too long: every part-th tile of the frame, 1 spp
+            part = int(min(4096, max(2, round(full_1spp / args.cpu_seconds))))
+            spp = 1
+        else:
+            part = 1
+            spp = max(1, min(4096, int(args.cpu_seconds / max(full_1spp, 1e-9))))
+        seg, dt = run(1, 1 + spp, part)
+    tiles = "the whole frame" if part == 1 else f"every {part}th 32x32 tile of the frame"
     return {"value": seg / dt / 1e6, "unit": "Mrays/s", "cores": cores, "kind": "port",
-            "sample": f"{scene_name} {w}x{h}, {spp} spp of the frame (samples 1..{spp}), max depth {max_depth}, "
+            "sample": f"{scene_name} {w}x{h}, {tiles}, {spp} spp (samples 1..{spp}), max depth {max_depth}, "
                       f"{seg} segments in {dt:.2f} s; oracle = C++ port of the reference (Rust toolchain absent), "
                       "reference structure (flat list + BvhNode), recursive sample_ray, OpenMP dynamic over pixels"}, seg, dt
 
@@ -293,16 +301,16 @@ def main():
         prims_per_seg = sc.prim_tests / max(sc.segments, 1)
         prim_bytes_per_seg = sc.prim_bytes / max(sc.segments, 1)
         # per segment: 64 B per child-pair fetch + geometry bytes of the primitive tests
-        #            + ray read 32 B + hit write 8 B + queue entry read 4 B
-        bytes_per_seg = 64.0 * pairs_per_seg + prim_bytes_per_seg + 32 + 8 + 4
+        #            + ray read 32 B + hit write 8 B (identity slot mapping: no queue entry)
+        bytes_per_seg = 64.0 * pairs_per_seg + prim_bytes_per_seg + 32 + 8
         p_tim = scene.params(w, h, spp, seed=SEED, pool_size=args.pool, slices=args.slices, flags=rtw.RTW_RENDER_TIME_KERNELS)
         p_tim = rdist.partition(p_tim, rank, world) if world > 1 else p_tim
         stt = scene.render_device(cam, p_tim, accum.data_ptr(), stream.cuda_stream)
         ach = bytes_per_seg * stt.segments / (stt.ms_traverse * 1e-3) / 1e9
         seg_per_launch = stt.segments / max(stt.iterations, 1)
         # HBM-only variant: the wavefront-state bytes of the kernel alone — what must cross HBM
-        # when nodes + primitives are cache resident (ray 32 B read, hit 8 B written, queue entry 4 B read)
-        hbm_only = 44.0 * stt.segments / (stt.ms_traverse * 1e-3) / 1e9
+        # when nodes + primitives are cache resident (ray 32 B read, hit 8 B written)
+        hbm_only = 40.0 * stt.segments / (stt.ms_traverse * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
         if os.path.exists(tpath):
@@ -318,11 +326,11 @@ def main():
                     "prim_tests_per_segment": prims_per_seg, "launches": stt.iterations,
                     "mean_launch_ms": stt.ms_traverse / max(stt.iterations, 1),
                     "traverse_share_of_step": stt.ms_traverse / max(stt.ms_traverse + stt.ms_shade, 1e-9),
-                    "hbm_only": {"bytes_per_segment": 44.0, "achieved": hbm_only, "frac": hbm_only / peak},
+                    "hbm_only": {"bytes_per_segment": 40.0, "achieved": hbm_only, "frac": hbm_only / peak},
                     "note": ("scene is L1/L2 resident (%d B of nodes + primitives): the algorithmic node/primitive bytes are "
                              "served from cache, so `frac` is a cache-bandwidth figure against the HBM peak and may exceed 1; "
                              "`hbm_only` counts the wavefront-state bytes that do cross HBM (ncu traffic agrees). The kernel is "
-                             "issue-bound: see profiles/r01e_ncu_full_final.csv" % scene.build_stats.device_bytes)
+                             "issue-bound: see profiles/r01_final_ncu_summary.txt" % scene.build_stats.device_bytes)
                     if resident else "scene exceeds L2: node / primitive fetches are HBM traffic"}
 
     base = None

@@ -235,6 +235,20 @@ int rtw_render(rtw_scene *s, const rtw_camera *cam, const rtw_render_params *par
 int rtw_render_device(rtw_scene *s, const rtw_camera *cam, const rtw_render_params *params,
                       float *d_accum_rgb, void *stream, rtw_render_stats *stats);
 
+/* ---- animation: one resident scene, many cameras (scenes.rs:622-667, main.rs:48-95) ------------ */
+/* The reference renders `cams` one after the other over the same world (main.rs:48) and writes a PNG per
+ * frame.  rtw_render_frames keeps the scene and its LBVH on the device and renders frame i with cameras[i]
+ * and the stream seed params->seed + i.  A finished frame is copied to pinned host memory on a copy stream
+ * and handed to `on_frame` on a helper thread while the device is already rendering the next one (two
+ * buffers in flight), so PNG encoding / ProgressMessage streaming overlaps the rendering.
+ * Callbacks arrive one at a time, in frame order; accum_rgb (layout as in rtw_render) and stats are valid
+ * only during the call.  A non-zero return value stops the animation after the frames already in flight.
+ * on_frame may be NULL (frames are rendered and dropped: benchmarking).  Returns the number of frames whose
+ * callback ran (or that were rendered, when on_frame is NULL), < 0 on error. */
+typedef int (*rtw_frame_callback)(void *user, uint32_t frame, const float *accum_rgb, const rtw_render_stats *stats);
+int rtw_render_frames(rtw_scene *s, const rtw_camera *cameras, uint32_t n_frames, const rtw_render_params *params,
+                      rtw_frame_callback on_frame, void *user);
+
 /* console_app/src/main.rs:73-86: c = sqrt(sum/spp); (255.999 * clamp(c, 0, 0.999)) as u8.
  * accum_rgb as above, rgb8 = width*height*3 bytes, same pixel order (top row first). */
 int rtw_resolve_rgb8(rtw_scene *s, const float *accum_rgb, uint32_t width, uint32_t height,

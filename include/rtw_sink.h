@@ -48,6 +48,8 @@ typedef struct rtw_sink {
   int (*add_triangles)(void *s, uint32_t n, const float *v, const float *nrm, const float *uv, const int32_t *mats, int material);
   int (*build)(void *s, float time0, float time1, rtw_build_stats *stats);
   int (*render)(void *s, const rtw_camera *cam, const rtw_render_params *p, float *accum_rgb, rtw_render_stats *stats);
+  int (*render_frames)(void *s, const rtw_camera *cams, uint32_t n_frames, const rtw_render_params *p,
+                       rtw_frame_callback on_frame, void *user);
 } rtw_sink;
 
 /* Fill `out` from the shared library at `path`, looking every entry point up as <prefix><name>
@@ -56,6 +58,26 @@ typedef struct rtw_sink {
 int rtwh_sink_open(const char *path, const char *prefix, int device, rtw_sink *out);
 int rtwh_sink_close(rtw_sink *sink); /* destroys the scene and closes the library */
 const char *rtwh_last_error(void);
+
+/* ---- ProgressMessage stream (lib.rs:128-138) in the wire format of the untouched host receivers ------------
+ * discovery_app serialises ProgressMessage with postcard 0.7.3 `to_vec_cobs` (discovery_app/src/bin/raytracer.rs:
+ * 62,105,111) and discovery_host_receiver decodes it with `from_bytes_cobs` (src/main.rs:37).  postcard 0.7 (pinned
+ * in Cargo.lock; the crate is not vendored, its published format is restated here): enum variant index = varint,
+ * u32 / f32 = 4 bytes little endian, [f32; 3] = 12 bytes; then COBS framing + one 0x00 terminator.
+ *   ImageStart{width, height, samples_per_pixel} -> 00 | w | h | spp          (13 bytes before COBS)
+ *   Pixel(Pixel{row, column, color})             -> 01 | row | column | r g b  (21 bytes before COBS)
+ *   ImageEnd                                     -> 02
+ * Each function writes one framed message to `out` (capacity `cap`) and returns its length, or RTW_ERR_INVALID
+ * when `cap` is too small (32 bytes always suffice). */
+int rtwh_progress_image_start(uint32_t width, uint32_t height, uint32_t samples_per_pixel, uint8_t *out, size_t cap);
+int rtwh_progress_pixel(uint32_t row, uint32_t column, const float color[3], uint8_t *out, size_t cap);
+int rtwh_progress_image_end(uint8_t *out, size_t cap);
+/* A whole frame as the reference would stream it: ImageStart, one Pixel per pixel in the order of lib.rs:58
+ * ((0..h).rev() x (0..w), the order of accum_rgb), ImageEnd.  Returns the bytes written (size the buffer with
+ * rtwh_progress_frame_bound) or RTW_ERR_INVALID. */
+size_t rtwh_progress_frame_bound(uint32_t width, uint32_t height);
+long long rtwh_progress_frame(const float *accum_rgb, uint32_t width, uint32_t height, uint32_t samples_per_pixel,
+                              uint8_t *out, size_t cap);
 
 #ifdef __cplusplus
 }

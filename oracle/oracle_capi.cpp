@@ -623,6 +623,26 @@ int orc_render(orc_scene* s, const rtw_camera* cam, const rtw_render_params* p, 
   return orc_render_ex(s, cam, p, accum_rgb, stats, 0, 0, 0);
 }
 
+// same signature as rtw_render_frames: frame i = cameras[i], seed + i; frames and callbacks strictly in order
+// (the checker has nothing to overlap)
+int orc_render_frames(orc_scene* s, const rtw_camera* cameras, uint32_t n_frames, const rtw_render_params* params,
+                      rtw_frame_callback on_frame, void* user) {
+  if (!s || !s->built) return fail(RTW_ERR_STATE, "render_frames: scene not built");
+  if (!params || (n_frames && !cameras)) return fail(RTW_ERR_INVALID, "render_frames: NULL argument");
+  std::vector<float> accum((size_t)params->width * params->height * 3);
+  int delivered = 0;
+  for (uint32_t f = 0; f < n_frames; ++f) {
+    rtw_render_params p = *params;
+    p.seed = params->seed + f;
+    rtw_render_stats st;
+    int rc = orc_render(s, &cameras[f], &p, accum.data(), &st);
+    if (rc != RTW_OK) return rc;
+    delivered++;
+    if (on_frame && on_frame(user, f, accum.data(), &st) != 0) break;
+  }
+  return delivered;
+}
+
 // Capture the ray batch that enters bounce `bounce` of sample `sample` of every pixel (bounce 0 =
 // camera rays).  Paths that ended earlier yield a null ray (t_max < t_min, never hits).
 // rays: width*height entries in the reference's pixel order.

@@ -28,6 +28,7 @@ RTW_TRACE_BVH = 0
 RTW_TRACE_BRUTE = 1
 RTW_RENDER_COUNT_TRAVERSAL = 1
 RTW_RENDER_TIME_KERNELS = 2
+RTW_OK, RTW_ERR_INVALID, RTW_ERR_CUDA, RTW_ERR_NOMEM, RTW_ERR_UNSUPPORTED, RTW_ERR_STATE = 0, -1, -2, -3, -4, -5
 
 RAY_DTYPE = np.dtype([("origin", "<f4", 3), ("direction", "<f4", 3), ("time", "<f4"), ("t_min", "<f4"), ("t_max", "<f4")])
 HIT_DTYPE = np.dtype([("prim_id", "<i4"), ("material_id", "<i4"), ("t", "<f4"), ("p", "<f4", 3), ("normal", "<f4", 3),
@@ -63,6 +64,10 @@ class RenderStats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
 
 
+# rtw_frame_callback (include/rtw_cuda.h)
+FRAME_CALLBACK = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.POINTER(C.c_float), C.POINTER(RenderStats))
+
+
 class BuildStats(C.Structure):
     _fields_ = [("num_prims", C.c_uint32), ("num_nodes", C.c_uint32), ("max_depth", C.c_uint32),
                 ("num_instances", C.c_uint32), ("ms_build", C.c_float), ("ms_upload", C.c_float),
@@ -76,7 +81,7 @@ _SINK_FUNCS = ["last_error", "scene_create", "scene_destroy", "add_texture_solid
                "add_texture_noise", "add_texture_uvdebug", "add_texture_image", "add_material_lambertian",
                "add_material_metal", "add_material_dielectric", "add_material_diffuse_light", "push_translation",
                "push_rotation_y", "pop_transform", "begin_group", "end_group", "begin_medium", "end_medium", "add_sphere", "add_moving_sphere",
-               "add_xy_rect", "add_xz_rect", "add_yz_rect", "add_cuboid", "add_triangles", "build", "render"]
+               "add_xy_rect", "add_xz_rect", "add_yz_rect", "add_cuboid", "add_triangles", "build", "render", "render_frames"]
 
 
 class Sink(C.Structure):
@@ -140,6 +145,8 @@ class Backend:
         f("trace_closest").argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int]
         f("render").argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(RenderParams), C.c_void_p, C.POINTER(RenderStats)]
         f("resolve_rgb8").argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+        f("render_frames").argtypes = [C.c_void_p, C.POINTER(Camera), C.c_uint32, C.POINTER(RenderParams), FRAME_CALLBACK,
+                                       C.c_void_p]
         if self.has("render_device"):
             f("render_device").argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(RenderParams), C.c_void_p, C.c_void_p,
                                            C.POINTER(RenderStats)]
@@ -197,9 +204,29 @@ def host_lib():
         h.rtwh_perlin_new.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         h.rtwh_load_obj.argtypes = [C.c_char_p, C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        h.rtwh_progress_image_start.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t]
+        h.rtwh_progress_pixel.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_float), C.c_void_p, C.c_size_t]
+        h.rtwh_progress_image_end.argtypes = [C.c_void_p, C.c_size_t]
+        h.rtwh_progress_frame_bound.argtypes = [C.c_uint32, C.c_uint32]
+        h.rtwh_progress_frame_bound.restype = C.c_size_t
+        h.rtwh_progress_frame.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t]
+        h.rtwh_progress_frame.restype = C.c_longlong
         h.rtwh_set_asset_dir(ASSET_DIR.encode())
         _host_lib = h
     return _host_lib
+
+
+def progress_frame(accum: np.ndarray, spp: int) -> bytes:
+    """A frame as the reference's ProgressMessage stream (lib.rs:128-138) in the host receivers' wire format
+    (postcard 0.7 + COBS, include/rtw_sink.h): ImageStart, one Pixel per pixel in lib.rs:58 order, ImageEnd."""
+    a = np.ascontiguousarray(accum, np.float32)
+    hgt, wid = a.shape[0], a.shape[1]
+    hl = host_lib()
+    buf = np.zeros(hl.rtwh_progress_frame_bound(wid, hgt), np.uint8)
+    n = hl.rtwh_progress_frame(a.ctypes.data, wid, hgt, spp, buf.ctypes.data, buf.size)
+    if n < 0:
+        raise RtwError(hl.rtwh_capi_error().decode())
+    return buf[:n].tobytes()
 
 
 def scene_names():
@@ -400,6 +427,28 @@ class Scene:
         st = RenderStats()
         self._c("render_device", C.byref(cam), C.byref(params), C.c_void_p(d_accum_ptr), C.c_void_p(stream), C.byref(st))
         return st
+
+    def render_frames(self, cams, params: RenderParams, on_frame=None) -> int:
+        """rtw_render_frames: frame i = cams[i], seed params.seed + i, over the resident scene.
+        on_frame(frame_no, accum[h, w, 3] (a copy), stats dict) -> truthy to continue; called in frame order on a
+        helper thread while the next frame renders.  Returns the number of frames delivered."""
+        arr = (Camera * len(cams))(*cams)
+        h, w = params.height, params.width
+        errors = []
+
+        def tramp(_user, frame, accum, stats):
+            try:
+                a = np.ctypeslib.as_array(accum, shape=(h, w, 3)).copy()
+                return 0 if (on_frame(int(frame), a, stats.contents.as_dict()) is not False) else 1
+            except Exception as e:  # never unwind through the C ABI
+                errors.append(e)
+                return 1
+
+        cb = FRAME_CALLBACK(tramp) if on_frame else C.cast(None, FRAME_CALLBACK)
+        n = self._c("render_frames", arr, len(cams), C.byref(params), cb, None)
+        if errors:
+            raise errors[0]
+        return n
 
     def resolve_rgb8(self, accum: np.ndarray, spp: int) -> np.ndarray:
         a = np.ascontiguousarray(accum, np.float32)

@@ -2,7 +2,9 @@
 // SoA arrays in canonical primitive order + instance chains) and thin wrappers that move host
 // buffers to the device and call the kernels.  No CPU fallback exists: every compute entry
 // point needs a CUDA device and fails with RTW_ERR_CUDA otherwise.
+#include <algorithm>
 #include <cmath>
+#include <future>
 #include <cstring>
 #include <string>
 
@@ -519,6 +521,91 @@ int rtw_render(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* par
   }
   cudaFree(d_accum);
   return rc;
+}
+
+// scenes.rs:622-667 + main.rs:48-95: every camera over one resident world; D2H of frame i and its callback
+// overlap the rendering of frame i+1.
+int rtw_render_frames(rtw_scene* s, const rtw_camera* cameras, uint32_t n_frames, const rtw_render_params* params,
+                      rtw_frame_callback on_frame, void* user) {
+  CHECK_BUILT(s);
+  if (!params || (n_frames && !cameras)) return set_error(RTW_ERR_INVALID, "render_frames: NULL argument");
+  if (n_frames == 0) return 0;
+  RTW_CUDA_TRY(cudaSetDevice(s->device));
+  const size_t bytes = std::max<size_t>((size_t)params->width * params->height * 3 * sizeof(float), 4);
+  float* d_accum[2] = {nullptr, nullptr};
+  float* h_accum[2] = {nullptr, nullptr};
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copied[2] = {nullptr, nullptr};
+  rtw_render_stats stats[2];
+  std::future<int> pending[2];  // callback of the frame that last used buffer b
+  int rc = RTW_OK, delivered = 0;
+  bool stop = false;
+  auto cleanup = [&]() {
+    for (auto& f : pending)
+      if (f.valid()) f.wait();
+    for (int b = 0; b < 2; ++b) {
+      cudaFree(d_accum[b]);
+      if (h_accum[b]) cudaFreeHost(h_accum[b]);
+      if (copied[b]) cudaEventDestroy(copied[b]);
+    }
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+  };
+  cudaError_t e = cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking);
+  for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+    e = cudaMalloc((void**)&d_accum[b], bytes);
+    if (e == cudaSuccess && on_frame) e = cudaMallocHost((void**)&h_accum[b], bytes);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    cleanup();
+    return set_error(RTW_ERR_NOMEM, std::string("render_frames: allocation failed: ") + cudaGetErrorString(e));
+  }
+  std::shared_future<void> previous;  // callbacks run one at a time, in frame order
+  for (uint32_t f = 0; f < n_frames && !stop; ++f) {
+    const int b = (int)(f & 1u);
+    if (pending[b].valid()) {  // buffer b is free once the callback of frame f-2 has returned
+      if (pending[b].get() != 0) stop = true;
+      delivered++;
+      if (stop) break;
+    }
+    rtw_render_params p = *params;
+    p.seed = params->seed + f;
+    rc = render_device(s, &cameras[f], &p, d_accum[b], 0, &stats[b]);  // returns when the frame is complete on the device
+    if (rc != RTW_OK) break;
+    if (!on_frame) {
+      delivered++;
+      continue;
+    }
+    e = cudaMemcpyAsync(h_accum[b], d_accum[b], bytes, cudaMemcpyDeviceToHost, copy_stream);
+    if (e == cudaSuccess) e = cudaEventRecord(copied[b], copy_stream);
+    if (e != cudaSuccess) {
+      rc = cuda_fail(e, "render_frames readback");
+      break;
+    }
+    std::shared_future<void> prev = previous;
+    std::promise<void> done;
+    previous = done.get_future().share();
+    const int device = s->device;
+    cudaEvent_t ev = copied[b];
+    const float* host = h_accum[b];
+    const rtw_render_stats* st = &stats[b];
+    pending[b] = std::async(std::launch::async, [=, done = std::move(done)]() mutable {
+      cudaSetDevice(device);
+      cudaEventSynchronize(ev);
+      if (prev.valid()) prev.wait();
+      int r = on_frame(user, f, host, st);
+      done.set_value();
+      return r;
+    });
+  }
+  for (auto& f : pending)
+    if (f.valid()) {
+      f.get();
+      delivered++;
+    }
+  cleanup();
+  return rc != RTW_OK ? rc : delivered;
 }
 
 int rtw_resolve_rgb8(rtw_scene* s, const float* accum_rgb, uint32_t width, uint32_t height, uint32_t spp, uint8_t* rgb8) {

@@ -67,6 +67,8 @@ bool save_png(const std::string& path, const uint8_t* rgb, uint32_t w, uint32_t 
           "  -s, --samples-per-pixel <SPP>          [default: 100]\n"
           "      --backend <cuda>                   [default: cuda]\n"
           "      --seed <N>  --device <D>  --lib <librtw_cuda.so>  --out-dir <DIR>\n"
+          "      --progress-out <FILE>   also write the frames as a ProgressMessage stream (postcard + COBS,\n"
+          "                              the wire format of discovery_host_receiver)\n"
           "SCENES:");
   for (const auto& n : rtwh::scene_names()) fprintf(stderr, " %s", n.c_str());
   fprintf(stderr, "\n");
@@ -78,7 +80,7 @@ bool save_png(const std::string& path, const uint8_t* rgb, uint32_t w, uint32_t 
 int main(int argc, char** argv) {
   uint32_t width = 400, spp = 100;
   double aspect_ratio = 1.7777778;
-  std::string backend = "cuda", scene, out_dir = "render", lib;
+  std::string backend = "cuda", scene, out_dir = "render", lib, progress_out;
   uint64_t seed = 1;
   int device = 0;
   for (int i = 1; i < argc; ++i) {
@@ -95,6 +97,7 @@ int main(int argc, char** argv) {
     else if (a == "--device") device = std::stoi(val());
     else if (a == "--lib") lib = val();
     else if (a == "--out-dir") out_dir = val();
+    else if (a == "--progress-out") progress_out = val();
     else if (a == "-h" || a == "--help") usage(nullptr);
     else if (!a.empty() && a[0] == '-') usage(("unknown option " + a).c_str());
     else scene = a;
@@ -117,41 +120,66 @@ int main(int argc, char** argv) {
   try {
     rtwh::World world = rtwh::generate_scene(scene, (float)image_width / (float)image_height, seed);
     mkdir(out_dir.c_str(), 0755);
-    int frame_no = 0;
-    for (const auto& cam : world.cameras) {  // main.rs:48
-      rtw_sink sink;
-      if (rtwh_sink_open(lib.c_str(), "rtw_", device, &sink) != RTW_OK) {
-        fprintf(stderr, "error: %s\n", rtwh_last_error());
-        return 1;
-      }
-      rtwh::Raytracer raytracer(world.objects, cam, world.background, image_width, image_height, spp);
-      rtw_render_stats st;
-      auto t0 = std::chrono::steady_clock::now();
-      std::vector<rtwh::Pixel> all_pixels = raytracer.render(&sink, seed, &st);
-      auto t1 = std::chrono::steady_clock::now();
-      rtwh_sink_close(&sink);
-      // main.rs:66-90
-      std::vector<uint8_t> img((size_t)image_width * image_height * 3);
-      float scale = 1.0f / (float)spp;
-      for (size_t i = 0; i < all_pixels.size(); ++i)
-        for (int c = 0; c < 3; ++c) {
-          float v = std::sqrt(scale * all_pixels[i].color.e[c]);
-          float cl = v < 0.0f ? 0.0f : (v > 0.999f ? 0.999f : v);
-          float b = 255.999f * cl;
-          img[3 * i + c] = (b != b || b <= 0.0f) ? 0 : (b >= 255.0f ? 255 : (uint8_t)b);
-        }
-      char name[64];
-      snprintf(name, sizeof(name), "/image_%04d.png", frame_no);
-      if (!save_png(out_dir + name, img.data(), image_width, image_height)) {
-        fprintf(stderr, "error: cannot write %s%s\n", out_dir.c_str(), name);
-        return 1;
-      }
-      double wall = std::chrono::duration<double>(t1 - t0).count();
-      fprintf(stderr, "frame %d: %ux%u, %u spp, %llu segments, GPU render %.1f ms (%.1f Mrays/s), wall %.3f s -> %s%s\n",
-              frame_no, image_width, image_height, spp, (unsigned long long)st.segments, st.ms_render,
-              st.ms_render > 0 ? st.segments / (st.ms_render * 1e3) : 0.0, wall, out_dir.c_str(), name);
-      ++frame_no;
+    // main.rs:48-95.  The reference builds a Raytracer per camera over the same world; the backend keeps that
+    // world resident (flattened + built once) and overlaps the PNG encoding of frame n with the rendering of n+1.
+    rtw_sink sink;
+    if (rtwh_sink_open(lib.c_str(), "rtw_", device, &sink) != RTW_OK) {
+      fprintf(stderr, "error: %s\n", rtwh_last_error());
+      return 1;
     }
+    FILE* progress = progress_out.empty() ? nullptr : fopen(progress_out.c_str(), "wb");
+    if (!progress_out.empty() && !progress) {
+      fprintf(stderr, "error: cannot write %s\n", progress_out.c_str());
+      return 1;
+    }
+    bool io_ok = true;
+    auto t0 = std::chrono::steady_clock::now();
+    uint32_t frames = rtwh::render_animation(
+        world, image_width, image_height, spp, &sink, seed,
+        [&](uint32_t frame_no, const std::vector<rtwh::Pixel>& all_pixels, const rtw_render_stats& st) {
+          // main.rs:66-90
+          std::vector<uint8_t> img((size_t)image_width * image_height * 3);
+          float scale = 1.0f / (float)spp;
+          for (size_t i = 0; i < all_pixels.size(); ++i)
+            for (int c = 0; c < 3; ++c) {
+              float v = std::sqrt(scale * all_pixels[i].color.e[c]);
+              float cl = v < 0.0f ? 0.0f : (v > 0.999f ? 0.999f : v);
+              float b = 255.999f * cl;
+              img[3 * i + c] = (b != b || b <= 0.0f) ? 0 : (b >= 255.0f ? 255 : (uint8_t)b);
+            }
+          char name[64];
+          snprintf(name, sizeof(name), "/image_%04u.png", frame_no);
+          if (!save_png(out_dir + name, img.data(), image_width, image_height)) {
+            fprintf(stderr, "error: cannot write %s%s\n", out_dir.c_str(), name);
+            io_ok = false;
+            return false;
+          }
+          if (progress) {  // lib.rs:128-138 as discovery_app streams it (raytracer.rs:62-111)
+            rtwh::ProgressMessage m;
+            m.kind = rtwh::ProgressMessage::ImageStart;
+            m.width = image_width; m.height = image_height; m.samples_per_pixel = spp;
+            std::vector<uint8_t> b = rtwh::to_vec_cobs(m);
+            fwrite(b.data(), 1, b.size(), progress);
+            m.kind = rtwh::ProgressMessage::PixelMsg;
+            for (const rtwh::Pixel& px : all_pixels) {
+              m.pixel = px;
+              b = rtwh::to_vec_cobs(m);
+              fwrite(b.data(), 1, b.size(), progress);
+            }
+            m.kind = rtwh::ProgressMessage::ImageEnd;
+            b = rtwh::to_vec_cobs(m);
+            fwrite(b.data(), 1, b.size(), progress);
+          }
+          fprintf(stderr, "frame %u: %ux%u, %u spp, %llu segments, GPU render %.1f ms (%.1f Mrays/s) -> %s%s\n", frame_no,
+                  image_width, image_height, spp, (unsigned long long)st.segments, st.ms_render,
+                  st.ms_render > 0 ? st.segments / (st.ms_render * 1e3) : 0.0, out_dir.c_str(), name);
+          return true;
+        });
+    double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (progress) fclose(progress);
+    rtwh_sink_close(&sink);
+    fprintf(stderr, "%u frame(s) in %.3f s (flatten + build + render + PNG)\n", frames, wall);
+    if (!io_ok) return 1;
   } catch (const std::exception& e) {
     fprintf(stderr, "error: %s\n", e.what());
     return 1;

@@ -138,4 +138,57 @@ int rtwh_load_obj(const char* path, uint32_t* ntris, float* verts, float* normal
   }
 }
 
+// ---- ProgressMessage wire format (include/rtw_sink.h) ----------------------------------------------------
+static int emit_message(const rtwh::ProgressMessage& m, uint8_t* out, size_t cap) {
+  std::vector<uint8_t> b = rtwh::to_vec_cobs(m);
+  if (!out || cap < b.size()) return fail(RTW_ERR_INVALID, "progress: output buffer too small");
+  memcpy(out, b.data(), b.size());
+  return (int)b.size();
+}
+int rtwh_progress_image_start(uint32_t width, uint32_t height, uint32_t spp, uint8_t* out, size_t cap) {
+  rtwh::ProgressMessage m;
+  m.kind = rtwh::ProgressMessage::ImageStart;
+  m.width = width; m.height = height; m.samples_per_pixel = spp;
+  return emit_message(m, out, cap);
+}
+int rtwh_progress_pixel(uint32_t row, uint32_t column, const float color[3], uint8_t* out, size_t cap) {
+  if (!color) return fail(RTW_ERR_INVALID, "progress: color is NULL");
+  rtwh::ProgressMessage m;
+  m.kind = rtwh::ProgressMessage::PixelMsg;
+  m.pixel.row = row; m.pixel.column = column;
+  m.pixel.color = rtwh::Color(color[0], color[1], color[2]);
+  return emit_message(m, out, cap);
+}
+int rtwh_progress_image_end(uint8_t* out, size_t cap) {
+  rtwh::ProgressMessage m;
+  m.kind = rtwh::ProgressMessage::ImageEnd;
+  return emit_message(m, out, cap);
+}
+size_t rtwh_progress_frame_bound(uint32_t width, uint32_t height) {
+  return 32 + (size_t)width * height * 24 + 8;  // COBS adds 1 byte per message below 254 bytes, postcard 1 terminator
+}
+long long rtwh_progress_frame(const float* accum_rgb, uint32_t width, uint32_t height, uint32_t spp, uint8_t* out, size_t cap) {
+  if (!accum_rgb || !out) return fail(RTW_ERR_INVALID, "progress: NULL buffer");
+  size_t n = 0;
+  auto put = [&](const rtwh::ProgressMessage& m) {
+    std::vector<uint8_t> b = rtwh::to_vec_cobs(m);
+    if (n + b.size() > cap) return false;
+    memcpy(out + n, b.data(), b.size());
+    n += b.size();
+    return true;
+  };
+  rtwh::ProgressMessage m;
+  m.kind = rtwh::ProgressMessage::ImageStart;
+  m.width = width; m.height = height; m.samples_per_pixel = spp;
+  if (!put(m)) return fail(RTW_ERR_INVALID, "progress: output buffer too small");
+  m.kind = rtwh::ProgressMessage::PixelMsg;
+  for (const rtwh::Pixel& px : rtwh::pixels_from_accum(accum_rgb, width, height)) {
+    m.pixel = px;
+    if (!put(m)) return fail(RTW_ERR_INVALID, "progress: output buffer too small");
+  }
+  m.kind = rtwh::ProgressMessage::ImageEnd;
+  if (!put(m)) return fail(RTW_ERR_INVALID, "progress: output buffer too small");
+  return (long long)n;
+}
+
 }  // extern "C"

@@ -76,6 +76,7 @@ int rtwh_sink_open(const char* path, const char* prefix, int device, rtw_sink* o
   RTW_BIND(add_triangles, "add_triangles");
   RTW_BIND(build, "build");
   RTW_BIND(render, "render");
+  RTW_BIND(render_frames, "render_frames");
 #undef RTW_BIND
   if (!missing.empty()) {
     dlclose(lib);
@@ -339,15 +340,112 @@ std::vector<Pixel> Raytracer::render(rtw_sink* sink, uint64_t seed, rtw_render_s
   std::vector<float> accum((size_t)w_ * h_ * 3);
   int rc = sink->render(sink->scene, &cam_.c, &p, accum.data(), stats);
   if (rc < 0) throw Error(std::string("render failed: ") + sink->last_error());
-  std::vector<Pixel> out((size_t)w_ * h_);
+  return pixels_from_accum(accum.data(), w_, h_);
+}
+
+std::vector<Pixel> pixels_from_accum(const float* accum, uint32_t w, uint32_t h) {
+  std::vector<Pixel> out((size_t)w * h);
   size_t i = 0;
-  for (uint32_t j = h_; j-- > 0;)  // (0..h).rev()
-    for (uint32_t col = 0; col < w_; ++col, ++i) {
+  for (uint32_t j = h; j-- > 0;)  // (0..h).rev()
+    for (uint32_t col = 0; col < w; ++col, ++i) {
       out[i].row = j;
       out[i].column = col;
       out[i].color = Color(accum[3 * i], accum[3 * i + 1], accum[3 * i + 2]);
     }
   return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// animation: main.rs:48-95 over a resident scene
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct AnimCtx {
+  const FrameFn* fn;
+  uint32_t w, h;
+  std::string error;
+};
+int anim_trampoline(void* user, uint32_t frame, const float* accum, const rtw_render_stats* st) {
+  AnimCtx* c = (AnimCtx*)user;
+  try {
+    return (*c->fn)(frame, pixels_from_accum(accum, c->w, c->h), *st) ? 0 : 1;
+  } catch (const std::exception& e) {  // never unwind through the C ABI
+    c->error = e.what();
+    return 1;
+  }
+}
+}  // namespace
+
+uint32_t render_animation(const World& world, uint32_t w, uint32_t h, uint32_t spp, rtw_sink* sink, uint64_t seed,
+                          const FrameFn& on_frame) {
+  flatten_world(world.objects, sink);
+  rtw_render_params p;
+  memset(&p, 0, sizeof(p));
+  p.width = w;
+  p.height = h;
+  p.spp = spp;
+  p.max_depth = 50;  // MAX_DEPTH (lib.rs:32)
+  p.background[0] = world.background.x(); p.background[1] = world.background.y(); p.background[2] = world.background.z();
+  p.seed = seed;
+  std::vector<rtw_camera> cams;
+  for (const auto& c : world.cameras) cams.push_back(c.c);
+  AnimCtx ctx{&on_frame, w, h, {}};
+  int rc = sink->render_frames(sink->scene, cams.data(), (uint32_t)cams.size(), &p, anim_trampoline, &ctx);
+  if (rc < 0) throw Error(std::string("render_frames failed: ") + sink->last_error());
+  if (!ctx.error.empty()) throw Error("frame callback failed: " + ctx.error);
+  return (uint32_t)rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ProgressMessage wire format: postcard 0.7.3 + COBS (include/rtw_sink.h)
+// ---------------------------------------------------------------------------------------------
+namespace {
+void put_u32(std::vector<uint8_t>& v, uint32_t x) {
+  for (int i = 0; i < 4; ++i) v.push_back((uint8_t)(x >> (8 * i)));
+}
+void put_f32(std::vector<uint8_t>& v, float f) {
+  uint32_t x;
+  memcpy(&x, &f, 4);
+  put_u32(v, x);
+}
+// Consistent Overhead Byte Stuffing (Cheshire & Baker 1999) + the terminating zero postcard appends
+std::vector<uint8_t> cobs_frame(const std::vector<uint8_t>& in) {
+  std::vector<uint8_t> out;
+  out.reserve(in.size() + in.size() / 254 + 2);
+  size_t code_at = 0;
+  out.push_back(0);
+  uint8_t code = 1;
+  for (uint8_t b : in) {
+    if (b == 0) {
+      out[code_at] = code;
+      code_at = out.size();
+      out.push_back(0);
+      code = 1;
+    } else {
+      out.push_back(b);
+      if (++code == 0xFF) {
+        out[code_at] = code;
+        code_at = out.size();
+        out.push_back(0);
+        code = 1;
+      }
+    }
+  }
+  out[code_at] = code;
+  out.push_back(0);
+  return out;
+}
+}  // namespace
+
+std::vector<uint8_t> to_vec_cobs(const ProgressMessage& m) {
+  std::vector<uint8_t> raw;
+  raw.push_back((uint8_t)m.kind);  // variant index as a varint: 0, 1, 2 are one byte
+  if (m.kind == ProgressMessage::ImageStart) {
+    put_u32(raw, m.width); put_u32(raw, m.height); put_u32(raw, m.samples_per_pixel);
+  } else if (m.kind == ProgressMessage::PixelMsg) {
+    put_u32(raw, m.pixel.row); put_u32(raw, m.pixel.column);
+    put_f32(raw, m.pixel.color.x()); put_f32(raw, m.pixel.color.y()); put_f32(raw, m.pixel.color.z());
+  }
+  return cobs_frame(raw);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdint>
 #include <map>
+#include <functional>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -371,6 +372,24 @@ class Raytracer {  // lib.rs:40-76 — Raytracer::new(world, cam, background, im
   Color bg_;
   uint32_t w_, h_, spp_;
 };
+
+// lib.rs:128-138
+struct ProgressMessage {
+  enum Kind : uint32_t { ImageStart = 0, PixelMsg = 1, ImageEnd = 2 } kind;
+  uint32_t width = 0, height = 0, samples_per_pixel = 0;  // ImageStart
+  Pixel pixel{};                                          // Pixel
+};
+// postcard 0.7.3 `to_vec_cobs` bytes of one message (see include/rtw_sink.h)
+std::vector<uint8_t> to_vec_cobs(const ProgressMessage& m);
+// the accumulation buffer of a frame as the reference's Pixel sequence ((0..h).rev() x (0..w), lib.rs:58)
+std::vector<Pixel> pixels_from_accum(const float* accum_rgb, uint32_t w, uint32_t h);
+
+// main.rs:48-95 for every camera of a world, with the scene kept resident on the backend (flattened and built
+// once): frame i = cameras[i], stream seed + i.  on_frame(frame_no, pixels, stats) runs on a helper thread while
+// the next frame renders; returning false stops the animation.  Returns the number of frames delivered.
+using FrameFn = std::function<bool(uint32_t, const std::vector<Pixel>&, const rtw_render_stats&)>;
+uint32_t render_animation(const World& world, uint32_t image_width, uint32_t image_height, uint32_t samples_per_pixel,
+                          rtw_sink* sink, uint64_t seed, const FrameFn& on_frame);
 
 // flatten a whole world (top-level list order = canonical order) and build it
 void flatten_world(const HittableList& world, rtw_sink* sink, float time0 = 0.f, float time1 = 1.f,

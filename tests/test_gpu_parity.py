@@ -266,3 +266,49 @@ def test_large_scene_mismatches_are_only_ill_conditioned_reference_hits(gpu, ora
         ok = ~bogus & ~diff
         assert np.array_equal(bits(hg["p"][ok]), bits(ho["p"][ok])) and np.array_equal(bits(hg["normal"][ok]), bits(ho["normal"][ok]))
         print(f"cull disagreements: {int(diff.sum())} of {n} rays ({int(bogus.sum())} ill-conditioned oracle hits)")
+
+
+def test_render_frames_keeps_the_scene_resident_and_matches_frame_by_frame(gpu, oracle):
+    """rtw_render_frames (scenes.rs:622-667 + main.rs:48-95): frame i = cameras[i], seed + i; callbacks in frame order;
+    bit-identical to one rtw_render per frame and to the oracle's frames (Cornell: no libm on the device path)."""
+    import threading
+    with rtw.Scene.from_name(gpu, "cornell-box", 1.0, seed=1) as sg, rtw.Scene.from_name(oracle, "cornell-box", 1.0, seed=1) as so:
+        cams = [sg.cameras[0], rtw.camera_new((278, 278, -700), (278, 278, 0), (0, 1, 0), 40.0, 1.0),
+                rtw.camera_new((100, 300, -600), (278, 278, 0), (0, 1, 0), 45.0, 1.0), sg.cameras[0]]
+        p = sg.params(48, 40, 5, seed=21, slices=2)
+        got, order, threads = {}, [], set()
+
+        def on_frame(i, accum, st):
+            order.append(i)
+            threads.add(threading.get_ident())
+            got[i] = (accum, st["segments"])
+
+        assert sg.render_frames(cams, p, on_frame) == 4
+        assert order == [0, 1, 2, 3]
+        assert threading.get_ident() not in threads          # delivered on the helper thread, overlapping the next render
+        for i, c in enumerate(cams):
+            a, st = sg.render(c, sg.params(48, 40, 5, seed=21 + i, slices=2))
+            assert np.array_equal(bits(a), bits(got[i][0])) and st.segments == got[i][1]
+            ao, sto = so.render(c, so.params(48, 40, 5, seed=21 + i, slices=2))
+            assert np.array_equal(bits(ao), bits(got[i][0])) and sto.segments == got[i][1]
+        assert not np.array_equal(got[0][0], got[3][0])      # same camera, another seed
+        # stopping: the frames already in flight (at most two) are still delivered, later ones are not rendered
+        seen = []
+        n = sg.render_frames(cams * 3, p, lambda i, a, st: (seen.append(i), False)[1])
+        assert 1 <= n <= 3 and seen == list(range(n))
+        assert sg.render_frames(cams, p, None) == 4          # no callback: frames rendered and dropped
+        with pytest.raises(rtw.RtwError):
+            sg.render_frames(cams, sg.params(1, 1, 1), on_frame)
+
+
+def test_tail_of_the_frame_switches_to_queues_and_stays_bit_exact(gpu, oracle):
+    """Identity slot mapping while work items remain, compaction queues afterwards (rtw_render.cu): frames far smaller
+    than, equal to and larger than the pool, all against the oracle."""
+    with rtw.Scene.from_name(gpu, "cornell-box", 1.0, seed=1) as sg, rtw.Scene.from_name(oracle, "cornell-box", 1.0, seed=1) as so:
+        cam = sg.cameras[0]
+        for (w, h, spp, pool, slices) in [(8, 8, 1, 0, 0), (33, 17, 3, 64, 2), (64, 64, 4, 4096, 1), (40, 40, 7, 1 << 20, 3)]:
+            pg = sg.params(w, h, spp, seed=9, pool_size=pool, slices=slices)
+            ag, stg = sg.render(cam, pg)
+            ao, sto = so.render(cam, so.params(w, h, spp, seed=9, slices=stg.slices))
+            assert stg.segments == sto.segments and stg.paths == w * h * spp
+            assert np.array_equal(bits(ag), bits(ao)), (w, h, spp, pool)

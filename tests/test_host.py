@@ -114,3 +114,89 @@ def test_console_app_cli():
     assert r.returncode == 2 and "missing scene" in r.stderr and "jumpy-balls" in r.stderr
     r = subprocess.run([exe, "-w", "8", "nope"], stderr=subprocess.PIPE, text=True, cwd=ROOT)
     assert r.returncode == 1 and "unknown scene" in r.stderr
+
+
+# ---- ProgressMessage stream (lib.rs:128-138) in the host receivers' wire format: postcard 0.7.3 + COBS --------------
+def _cobs_decode(frame: bytes) -> bytes:
+    """Independent COBS decoder (Cheshire & Baker); `frame` without its 0x00 terminator."""
+    out, i = bytearray(), 0
+    while i < len(frame):
+        code = frame[i]
+        assert code != 0
+        out += frame[i + 1:i + code]
+        i += code
+        if code != 0xFF and i < len(frame):
+            out.append(0)
+    return bytes(out)
+
+
+def test_progress_messages_known_answers():
+    import ctypes as C
+    h = rtw.host_lib()
+    buf = (C.c_uint8 * 64)()
+    # ImageEnd: variant 2, no payload -> raw 02 -> COBS 02 02, terminator 00
+    n = h.rtwh_progress_image_end(buf, 64)
+    assert bytes(buf[:n]) == b"\x02\x02\x00"
+    # ImageStart{32, 32, 50} (discovery_app/src/bin/raytracer.rs:55-66): raw = 00 | 20 00 00 00 | 20 00 00 00 | 32 00 00 00;
+    # COBS by hand: zero-separated groups "", "20", "", "", "20", "", "", "32", "", "", "" -> code = len + 1 each
+    n = h.rtwh_progress_image_start(32, 32, 50, buf, 64)
+    assert bytes(buf[:n]) == bytes.fromhex("01 02 20 01 01 02 20 01 01 02 32 01 01 01 00")
+    # Pixel{row 1, column 2, color (1.0, 0.5, -2.0)}: raw = 01 | 01 00 00 00 | 02 00 00 00 | 00 00 80 3f | 00 00 00 3f | 00 00 00 c0
+    col = (C.c_float * 3)(1.0, 0.5, -2.0)
+    n = h.rtwh_progress_pixel(1, 2, col, buf, 64)
+    raw = bytes.fromhex("01 01000000 02000000 0000803f 0000003f 000000c0")
+    assert buf[n - 1] == 0 and 0 not in bytes(buf[:n - 1])
+    assert _cobs_decode(bytes(buf[:n - 1])) == raw
+    assert bytes(buf[:n]) == bytes.fromhex("03 01 01 01 01 02 02 01 01 01 01 03 80 3f 01 01 02 3f 01 01 02 c0 00")
+    assert h.rtwh_progress_pixel(1, 2, col, buf, 8) == rtw.RTW_ERR_INVALID     # buffer too small
+
+
+def test_progress_frame_stream_decodes_to_the_pixel_order_of_the_reference():
+    import struct
+    rs = np.random.RandomState(5)
+    hgt, wid, spp = 5, 7, 9
+    accum = rs.uniform(0, 4, (hgt, wid, 3)).astype(np.float32)
+    accum[0, 0] = 0.0                       # zeros inside the payload exercise the byte stuffing
+    stream = rtw.progress_frame(accum, spp)
+    frames = stream.split(b"\x00")
+    assert frames[-1] == b"" and len(frames) == 1 + hgt * wid + 1 + 1
+    msgs = [_cobs_decode(f) for f in frames[:-1]]
+    assert msgs[0] == bytes([0]) + struct.pack("<III", wid, hgt, spp)
+    assert msgs[-1] == bytes([2])
+    k = 1
+    for y_top in range(hgt):                # (0..h).rev() x (0..w): top image row first, Pixel.row counts from the bottom
+        for col in range(wid):
+            tag, row, column, r, g, b = struct.unpack("<BIIfff", msgs[k])
+            assert (tag, row, column) == (1, hgt - 1 - y_top, col)
+            assert np.array_equal(np.float32([r, g, b]), accum[y_top, col])
+            k += 1
+
+
+def test_cobs_long_runs_without_zero():
+    # a 300-byte zero-free payload needs the 0xFF block split; no message of the protocol is that long, so the
+    # encoder is exercised through a frame whose pixel colours are chosen zero-free and checked by the decoder
+    accum = np.full((2, 200, 3), np.float32(1.2345678), np.float32)
+    stream = rtw.progress_frame(accum, 1)
+    frames = stream.split(b"\x00")[:-1]
+    assert len(frames) == 402
+    for f in frames[1:-1]:
+        raw = _cobs_decode(f)
+        assert len(raw) == 21 and raw[0] == 1
+
+
+def test_oracle_render_frames_equals_frame_by_frame(oracle):
+    with rtw.Scene.from_name(oracle, "cornell-box", 1.0, seed=1) as s:
+        cam = s.cameras[0]
+        cam2 = rtw.camera_new((278, 278, -700), (278, 278, 0), (0, 1, 0), 40.0, 1.0)
+        p = s.params(24, 24, 3, seed=11)
+        got = {}
+
+        def on_frame(i, accum, st):
+            got[i] = (accum, st["segments"])
+            return i < 1                    # stop after the second frame
+
+        n = s.render_frames([cam, cam2, cam], p, on_frame)
+        assert n == 2 and sorted(got) == [0, 1]
+        for i, c in enumerate([cam, cam2]):
+            a, st = s.render(c, s.params(24, 24, 3, seed=11 + i))
+            assert np.array_equal(a, got[i][0]) and st.segments == got[i][1]
