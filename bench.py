@@ -132,8 +132,9 @@ def cpu_baseline(args, scene_name, w, h, max_depth=50):
     orc = rtw.Backend(os.path.join(ROOT, "oracle", "liboracle.so"), "orc_")  # bench.py's cpu_baseline leg
     orc.fn("render_ex").argtypes = [C.c_void_p, C.POINTER(rtw.Camera), C.POINTER(rtw.RenderParams), C.c_void_p,
                                     C.POINTER(rtw.RenderStats), C.c_int, C.c_int, C.c_int]
-    orc.fn("num_threads").restype = C.c_int
-    cores = orc.fn("num_threads")()
+    # all host cores of the box, stated explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers, which would
+    # silently make the "all host threads" arm single-threaded
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     with rtw.Scene.from_name(orc, scene_name, w / h, seed=SEED) as so:
         cam = so.cameras[0]
         accum = np.zeros((h, w, 3), np.float32)
@@ -143,12 +144,16 @@ def cpu_baseline(args, scene_name, w, h, max_depth=50):
                           part_rank=0, part_count=part_count)
             st = rtw.RenderStats()
             t0 = time.perf_counter()
-            orc.check(orc.fn("render_ex")(so.h, C.byref(cam), C.byref(p), accum.ctypes.data, C.byref(st), 2, 1, 0), "render_ex")
+            orc.check(orc.fn("render_ex")(so.h, C.byref(cam), C.byref(p), accum.ctypes.data, C.byref(st), 2, 1, cores), "render_ex")
             return st.segments, time.perf_counter() - t0
 
-        # calibration: one sample per pixel on every 64th 32x32 tile (interleaved over the frame)
-        seg, dt = run(0, 1, 64)
-        full_1spp = dt * 64.0
+        # calibration: one sample per pixel on every 64th 32x32 tile (interleaved over the frame); a denser subset
+        # when that is too short to time
+        for cal in (64, 8, 1):
+            seg, dt = run(0, 1, cal)
+            if dt >= 0.3 or cal == 1:
+                break
+        full_1spp = dt * cal
         if full_1spp > args.cpu_seconds:  # a full-frame sample is too long: every part-th tile of the frame, 1 spp
             part = int(min(4096, max(2, round(full_1spp / args.cpu_seconds))))
             spp = 1

@@ -165,6 +165,9 @@ int rtw_add_material_diffuse_light(rtw_scene *s, int emit_texture);            /
  *   cuboid.rotate_y(15).translate(v)  ==  push_translation(v); push_rotation_y(15); add_cuboid; pop; pop */
 int rtw_push_translation(rtw_scene *s, const float offset[3]);   /* Translation  :16-48   */
 int rtw_push_rotation_y(rtw_scene *s, float angle_degrees);      /* YRotation    :50-153  */
+/* the same wrapper from the two values YRotation actually stores (sin_theta, cos_theta: transformations.rs:51-56,
+ * computed at :60-63) — what the Rust `flatten` hook passes, so that no libm call is repeated on this side */
+int rtw_push_rotation_y_sincos(rtw_scene *s, float sin_theta, float cos_theta);
 int rtw_pop_transform(rtw_scene *s);
 /* BvhNode::new(objects, ..) (bvh.rs:19-74) is an acceleration hint with no effect on results:
  * the backend always builds one LBVH over every primitive.  begin/end_group keep the call

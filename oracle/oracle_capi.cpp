@@ -116,7 +116,8 @@ void instantiate(orc_scene* s, const Desc& d, bool use_bvh, Rng& build_rng, std:
     }
     case D_ROTY: {
       std::unique_ptr<YRotation> r(new YRotation());
-      r->init(wrap_children(s, d, use_bvh, build_rng), d.f[0]);
+      if (d.f[3] != 0.f) r->init_sincos(wrap_children(s, d, use_bvh, build_rng), d.f[1], d.f[2]);
+      else r->init(wrap_children(s, d, use_bvh, build_rng), d.f[0]);
       out.push_back(HittablePtr(r.release()));
       break;
     }
@@ -382,6 +383,14 @@ int orc_push_rotation_y(orc_scene* s, float angle_degrees) {
   CHECK_SCENE(s);
   Desc* d = push_child(s, D_ROTY);
   d->f[0] = angle_degrees;
+  s->stack.push_back(d);
+  return RTW_OK;
+}
+int orc_push_rotation_y_sincos(orc_scene* s, float sin_theta, float cos_theta) {
+  CHECK_SCENE(s);
+  Desc* d = push_child(s, D_ROTY);
+  d->f[0] = 0.f;
+  d->f[1] = sin_theta; d->f[2] = cos_theta; d->f[3] = 1.f;  // f[3] != 0: take (sin, cos) as given
   s->stack.push_back(d);
   return RTW_OK;
 }

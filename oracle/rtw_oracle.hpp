@@ -683,6 +683,15 @@ struct YRotation : Hittable {  // transformations.rs:50-153
     has_box = inner->bounding_box(0.0f, 1.0f, b);
     if (has_box) bbox = rotate_bounding_box(b, sin_theta, cos_theta);
   }
+  // the struct as it is stored (transformations.rs:51-56): sin / cos given, box from them (:64-75)
+  void init_sincos(HittablePtr in, float s, float c) {
+    inner = std::move(in);
+    sin_theta = s;
+    cos_theta = c;
+    Aabb b;
+    has_box = inner->bounding_box(0.0f, 1.0f, b);
+    if (has_box) bbox = rotate_bounding_box(b, sin_theta, cos_theta);
+  }
   // transformations.rs:115-148
   bool hit(const Ray& r, float t_min, float t_max, Rng& rng, HitRecord& out) const override {
     Point3 origin = r.origin;

@@ -128,6 +128,7 @@ class Backend:
         f("add_material_diffuse_light").argtypes = [C.c_void_p, C.c_int]
         f("push_translation").argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         f("push_rotation_y").argtypes = [C.c_void_p, C.c_float]
+        f("push_rotation_y_sincos").argtypes = [C.c_void_p, C.c_float, C.c_float]
         f("pop_transform").argtypes = [C.c_void_p]
         f("begin_group").argtypes = [C.c_void_p]
         f("end_group").argtypes = [C.c_void_p]
@@ -350,6 +351,7 @@ class Scene:
     def diffuse_light_rgb(self, r, g, b): return self.diffuse_light(self.texture_solid(r, g, b))
     def push_translation(self, off): return self._c("push_translation", _f3(off))
     def push_rotation_y(self, deg): return self._c("push_rotation_y", deg)
+    def push_rotation_y_sincos(self, s, c): return self._c("push_rotation_y_sincos", s, c)
     def pop_transform(self): return self._c("pop_transform")
     def begin_group(self): return self._c("begin_group")
     def end_group(self): return self._c("end_group")

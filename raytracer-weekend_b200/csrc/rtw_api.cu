@@ -244,6 +244,15 @@ int rtw_push_rotation_y(rtw_scene* s, float angle_degrees) {
   op.c = 0.f;
   return push_op(s, op);
 }
+int rtw_push_rotation_y_sincos(rtw_scene* s, float sin_theta, float cos_theta) {
+  CHECK_OPEN(s);
+  InstOp op;
+  op.kind = OP_ROTY;
+  op.a = sin_theta;
+  op.b = cos_theta;
+  op.c = 0.f;
+  return push_op(s, op);
+}
 int rtw_pop_transform(rtw_scene* s) {
   CHECK_OPEN(s);
   if (s->open_kinds.empty() || s->open_kinds.back() != 0) return set_error(RTW_ERR_STATE, "pop_transform: no open transform");

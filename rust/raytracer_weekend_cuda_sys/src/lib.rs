@@ -149,6 +149,7 @@ extern "C" {
     // ---- instance wrappers (hittable/transformations.rs), groups (bvh.rs), media (hittable/volumes.rs)
     pub fn rtw_push_translation(s: *mut rtw_scene, offset: *const f32) -> c_int;
     pub fn rtw_push_rotation_y(s: *mut rtw_scene, angle_degrees: f32) -> c_int;
+    pub fn rtw_push_rotation_y_sincos(s: *mut rtw_scene, sin_theta: f32, cos_theta: f32) -> c_int;
     pub fn rtw_pop_transform(s: *mut rtw_scene) -> c_int;
     pub fn rtw_begin_group(s: *mut rtw_scene) -> c_int;
     pub fn rtw_end_group(s: *mut rtw_scene) -> c_int;

@@ -170,3 +170,29 @@ def test_no_gpu_fails_loudly_no_fallback():
             s.build()
     with pytest.raises(rtw.RtwError):
         rtw.Scene.from_name(b, "cornell-box", 1.0)
+
+
+def test_rotation_from_stored_sin_cos_equals_rotation_from_angle(oracle):
+    """rtw_push_rotation_y_sincos takes what YRotation stores (transformations.rs:51-56); with sin / cos computed like
+    transformations.rs:60-63 the flattened instance and every hit are identical to rtw_push_rotation_y(angle)."""
+    import math
+    rays = rtw.make_rays(np.tile([[0.3, 0.2, -5]], (256, 1)), np.random.RandomState(1).uniform(-0.3, 0.3, (256, 3)) + [0, 0, 1])
+    hits = []
+    for use_sincos in (False, True):
+        s = oracle.new_scene()
+        m = s.lambertian_rgb(0.5, 0.5, 0.5)
+        s.push_translation((0.1, 0.2, 0.3))
+        if use_sincos:
+            rad = np.float32(15.0) * np.float32(np.float32(math.pi) / np.float32(180.0))
+            s.push_rotation_y_sincos(float(np.sin(rad, dtype=np.float32)), float(np.cos(rad, dtype=np.float32)))
+        else:
+            s.push_rotation_y(15.0)
+        s.cuboid((-1, -1, -1), (1, 1, 1), m)
+        s.pop_transform()
+        s.pop_transform()
+        s.build()
+        hits.append(s.trace_closest(rays))
+        s.close()
+    assert (hits[0]["prim_id"] >= 0).sum() > 50
+    np.testing.assert_allclose(hits[0]["t"], hits[1]["t"], rtol=2e-6)      # numpy's sinf may differ from glibc's by an ulp
+    assert np.array_equal(hits[0]["prim_id"], hits[1]["prim_id"])
