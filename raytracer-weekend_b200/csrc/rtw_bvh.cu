@@ -340,6 +340,30 @@ __global__ void k_karras(int n, const uint64_t* __restrict__ keys, uint32_t* __r
   node_range[i] = make_uint2((uint32_t)lo, (uint32_t)(hi - lo + 1));
 }
 
+// Kernel (one thread): the first `cap` pairs of the tree in breadth-first order, for the shared-memory top of
+// tree of the traversal kernels.  A child link that points to a pair inside the copy is re-targeted to its index
+// in the copy and tagged RTW_LINK_TOP; every other link (deeper pairs, leaves) is kept.
+__global__ void k_top_tree(const float4* __restrict__ nodes, uint32_t num_nodes, uint32_t cap, float4* __restrict__ top,
+                           uint32_t* __restrict__ top_src, uint32_t* __restrict__ top_count) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  uint32_t n = 0;
+  if (num_nodes > 0 && cap > 0) { top_src[0] = 0; n = 1; }
+  for (uint32_t t = 0; t < n; ++t) {
+    const float4* src = nodes + 4 * (size_t)top_src[t];
+    float4 rec[4] = {src[0], src[1], src[2], src[3]};
+    for (int c = 0; c < 2; ++c) {
+      const int32_t link = __float_as_int(rec[2 * c].w);
+      if (link >= 0 && n < cap) {
+        top_src[n] = (uint32_t)link;
+        rec[2 * c].w = __int_as_float((int32_t)(RTW_LINK_TOP | n));
+        n++;
+      }
+    }
+    for (int k = 0; k < 4; ++k) top[4 * (size_t)t + k] = rec[k];
+  }
+  *top_count = n;
+}
+
 // Kernel: leaves.  Slot s holds primitive vals[s]; copies its geometry and meta into slot order.
 __global__ void k_emit_leaves(uint32_t n, const uint32_t* __restrict__ vals, const float4* __restrict__ enc,
                               const uint32_t* __restrict__ meta, const uint32_t* __restrict__ prim_mat,
@@ -630,6 +654,20 @@ int build_scene_device(rtw_scene* s, float time0, float time1, rtw_build_stats* 
                     d_nodes, d_root, d_info);
   if (n > 1) k_sort_leaf_ranges<<<G, T>>>(n - 1, d_collapsed, d_nparent, d_nrange, d.prim_meta, d_v0);
   k_emit_leaves<<<G, T>>>(n, d_v0, d_enc, d.prim_meta, d.prim_mat, d.prim_shade, d_geom, d_slot_prim, d_slot_meta, d_slot_ms);
+  d.top_nodes = nullptr;
+  d.top_count = 0;
+#if RTW_TOP_TREE > 0
+  {
+    float4* d_top;
+    uint32_t *d_top_src, *d_top_count;
+    if ((rc = dev_alloc(s, &d_top, 4 * (size_t)RTW_TOP_TREE))) return rc;
+    if ((rc = dev_alloc(s, &d_top_src, (size_t)RTW_TOP_TREE + 1))) return rc;
+    d_top_count = d_top_src + RTW_TOP_TREE;
+    k_top_tree<<<1, 32>>>(d_nodes, d.num_nodes, RTW_TOP_TREE, d_top, d_top_src, d_top_count);
+    RTW_CUDA_TRY(cudaMemcpy(&d.top_count, d_top_count, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    d.top_nodes = d_top;
+  }
+#endif
   RTW_CUDA_TRY(cudaGetLastError());
   RTW_CUDA_TRY(cudaEventRecord(ev[2]));
   RTW_CUDA_TRY(cudaEventSynchronize(ev[2]));

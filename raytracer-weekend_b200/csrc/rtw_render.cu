@@ -266,7 +266,13 @@ __global__ void __launch_bounds__(128, (COUNT || MEDIA) ? 1 : RTW_TRAVERSE_MINBL
   const uint32_t lane = threadIdx.x & 31;
   TraverseCounters cnt;
   WaveIO io{w, in_queue ? w.queue[parity] : nullptr, 0, seed_lo, seed_hi, false};
+#if RTW_TOP_TREE > 0
+  __shared__ float4 top_smem[4 * RTW_TOP_TREE];
+  stage_top_tree(sc, top_smem);
+  traverse_persistent<COUNT, MEDIA>(sc, io, count, &ctl->cursor_traverse, cnt, top_smem);
+#else
   traverse_persistent<COUNT, MEDIA>(sc, io, count, &ctl->cursor_traverse, cnt);
+#endif
   if (COUNT) {
     uint32_t p = cnt.pairs, q = cnt.prims, r = cnt.prim_bytes;
     for (int off = 16; off > 0; off >>= 1) {

@@ -56,7 +56,13 @@ __global__ void __launch_bounds__(128) k_trace_bvh(SceneDev sc, const rtw_ray* _
                                                    rtw_hit* __restrict__ hits, uint32_t* cursor) {
   BatchIO io{sc, rays, hits};
   TraverseCounters cnt;
+#if RTW_TOP_TREE > 0
+  __shared__ float4 top_smem[4 * RTW_TOP_TREE];
+  stage_top_tree(sc, top_smem);
+  traverse_persistent<false, MEDIA>(sc, io, n, cursor, cnt, top_smem);
+#else
   traverse_persistent<false, MEDIA>(sc, io, n, cursor, cnt);
+#endif
 }
 
 __global__ void __launch_bounds__(128) k_trace_brute(SceneDev sc, const rtw_ray* __restrict__ rays, uint64_t n,

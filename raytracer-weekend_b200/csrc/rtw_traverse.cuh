@@ -87,10 +87,23 @@ struct TraverseCounters {
 //   void rng_key(Rng& rng)   (pixel, sample, stage, seed) of the current ray — only called when a medium is tested
 // MEDIA = the scene contains ConstantMedium primitives (compiled out otherwise: the keyed draw and the
 // boundary tests cost registers and branches in the hottest loop).
+// Stage the top of the tree (rtw_bvh.cu: k_top_tree) in shared memory; call with the whole block.
+__device__ __forceinline__ void stage_top_tree(const SceneDev& sc, float4* top_smem) {
+#if RTW_TOP_TREE > 0
+  for (uint32_t i = threadIdx.x; i < 4u * sc.top_count; i += blockDim.x) top_smem[i] = sc.top_nodes[i];
+  __syncthreads();
+#endif
+}
+
 template <bool COUNT, bool MEDIA, class IO>
 __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, uint32_t count, uint32_t* cursor,
-                                                    TraverseCounters& cnt) {
+                                                    TraverseCounters& cnt, const float4* top_smem = nullptr) {
   const uint32_t lane = threadIdx.x & 31;
+#if RTW_TOP_TREE > 0
+  const int32_t root_link = sc.top_count ? (int32_t)RTW_LINK_TOP : 0;
+#else
+  const int32_t root_link = 0;
+#endif
   const uint32_t lane_lt = (1u << lane) - 1u;
   bool active = false;
   bool resumed = false;    // this ray was suspended by the previous launch: finish it
@@ -154,7 +167,7 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
           best_t = t_max; best_slot = slot0; best_id = -2;
           best_meta = slot0 >= 0 ? __ldg(sc.slot_meta + slot0) : 0u;
           oi = o; di = d; cur_inst = 0; cur_pm = 0xffffffffu;
-          sp = 0; link = 0; meta = 0; pl_meta = 0;
+          sp = 0; link = root_link; meta = 0; pl_meta = 0;
           active = true;
         }
       }
@@ -192,8 +205,15 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
         break;
 #endif
       if (searching) {
+#if RTW_TOP_TREE > 0
+        // generic loads: the pair lies in shared memory (top of the tree) or in global memory
+        const float4* n = (link & RTW_LINK_TOP) ? top_smem + 4 * (size_t)(link & (RTW_LINK_TOP - 1))
+                                                : sc.nodes + 4 * (size_t)link;
+        const float4 l0 = n[0], l1 = n[1], r0 = n[2], r1 = n[3];
+#else
         const float4* __restrict__ n = sc.nodes + 4 * (size_t)link;
         const float4 l0 = __ldg(n), l1 = __ldg(n + 1), r0 = __ldg(n + 2), r1 = __ldg(n + 3);
+#endif
         if (COUNT) cnt.pairs++;
         float tl, tr;
         const bool hl = slab(l0, l1, o, inv, t_min, best_t, tl);
