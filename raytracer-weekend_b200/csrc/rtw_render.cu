@@ -57,7 +57,7 @@ struct WaveDev {
   float4* sum;      // running slice sum rgb
   uint4* state;     // pixel index (row*w+col), sample, sample_end, bounce | slice << 8
   uint32_t* queue[2];
-  float4* partial;  // [slices][w*h] slice sums (slices > 1)
+  float4* partial;  // [slices][pix_per_slice] slice sums of the pixels this partition owns (slices > 1)
   WaveCtl* ctl;                      // this sub-pool's counters
   unsigned long long* item_cursor;   // shared by all sub-pools
   uint32_t* exhausted;               // shared by all sub-pools
@@ -133,6 +133,21 @@ __device__ __forceinline__ bool decode_item(const FrameDev& f, unsigned long lon
   it.pixel = row * f.width + x;
   it.slice = k;
   return it.sample_end > it.sample;
+}
+
+// Index of an owned pixel inside a slice = the `q` decode_item splits (tile-major over the owned tiles): the slice
+// sums are stored compactly, [slices][pix_per_slice], whatever share of the frame this partition renders.
+__device__ __forceinline__ unsigned long long owned_index(const FrameDev& f, uint32_t x, uint32_t y_top) {
+  uint32_t tx, ty, wx, wy;
+  if (f.tile_shift != 0xffffffffu) {
+    tx = x >> f.tile_shift; ty = y_top >> f.tile_shift;
+    wx = x & (f.tile_size - 1u); wy = y_top & (f.tile_size - 1u);
+  } else {
+    tx = x / f.tile_size; ty = y_top / f.tile_size;
+    wx = x - tx * f.tile_size; wy = y_top - ty * f.tile_size;
+  }
+  const uint32_t tile_local = (ty * f.tiles_x + tx) / f.part_count;
+  return (unsigned long long)tile_local * (f.tile_size * f.tile_size) + wy * f.tile_size + wx;
 }
 
 // Warp-cooperative fetch: every lane with `need` gets a valid item or learns that none are left.
@@ -430,7 +445,8 @@ __global__ void __launch_bounds__(128) k_wave_shade(
           if (f.slices == 1) {
             accum[3 * pix] = sum.x; accum[3 * pix + 1] = sum.y; accum[3 * pix + 2] = sum.z;
           } else {
-            w.partial[(size_t)(st.w >> 8) * f.width * f.height + pix] = make_float4(sum.x, sum.y, sum.z, 0.f);
+            w.partial[(size_t)(st.w >> 8) * f.pix_per_slice + owned_index(f, col, f.height - 1 - row)] =
+                make_float4(sum.x, sum.y, sum.z, 0.f);
           }
           it.slice = RTW_NEED_ITEM;
         }
@@ -474,8 +490,9 @@ __global__ void k_wave_resolve(FrameDev f, const float4* __restrict__ partial, f
     uint32_t tile = (y_top / f.tile_size) * f.tiles_x + (x / f.tile_size);
     v3 acc = mk(0.f, 0.f, 0.f);
     if (tile % f.part_count == f.part_rank) {
+      const unsigned long long q = owned_index(f, x, y_top);
       for (uint32_t k = 0; k < f.slices; ++k) {
-        float4 s = partial[(size_t)k * npix + pix];
+        float4 s = partial[(size_t)k * f.pix_per_slice + q];
         acc = acc + mk(s.x, s.y, s.z);
       }
     }
@@ -591,7 +608,11 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
   if (slices == 0) {  // enough items that the last ones to finish are a small fraction of the frame
     unsigned long long want = 16ull * pool;
     unsigned long long per = std::max<unsigned long long>(f.pix_per_slice, 1);
-    slices = (uint32_t)std::min<unsigned long long>((want + per - 1) / per, 64ull);
+    // as many slices as it takes for 16 items per slot — a slot runs the samples of its item one after the other,
+    // so coarse items leave a large pool idle behind a few long chains (8-way partition of Cornell: 105 ms at 64
+    // slices vs 72 ms ideal) — bounded by the slice-sum buffer (16 B per item, <= 4 GiB)
+    const unsigned long long cap = std::max<unsigned long long>((256ull << 20) / per, 1ull);
+    slices = (uint32_t)std::min<unsigned long long>((want + per - 1) / per, cap);
   }
   slices = std::max(1u, std::min(slices, std::max(nsamp, 1u)));
   if (slices > 0xFFFFFFu) return set_error(RTW_ERR_INVALID, "render: too many slices");
@@ -625,7 +646,7 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
     RTW_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wave_shade, 128, 0));
     wh->blocks_shade = std::max(nb, 1) * s->num_sms;
   }
-  const size_t partial_elems = slices > 1 ? (size_t)slices * npix : 0;
+  const size_t partial_elems = slices > 1 ? (size_t)slices * f.pix_per_slice : 0;
   if (wh->pool != pool || wh->partial_elems < partial_elems) {
     wave_release(wh);
     int rc;

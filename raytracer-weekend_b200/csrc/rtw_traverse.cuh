@@ -57,6 +57,9 @@ __device__ __forceinline__ bool slab(float4 lo, float4 hi, v3 o, v3 inv, float t
   return t_min <= t_far;
 }
 
+#ifndef RTW_TOP_TREE_GENERIC
+#define RTW_TOP_TREE_GENERIC 0
+#endif
 #ifndef RTW_CURSOR_CHUNKS
 #define RTW_CURSOR_CHUNKS 0  // A/B r01: private 32-entry chunks with a prefetched cursor are 3-13 % SLOWER (partial refills, drain imbalance)
 #endif
@@ -205,11 +208,20 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
         break;
 #endif
       if (searching) {
-#if RTW_TOP_TREE > 0
+#if RTW_TOP_TREE > 0 && RTW_TOP_TREE_GENERIC
         // generic loads: the pair lies in shared memory (top of the tree) or in global memory
         const float4* n = (link & RTW_LINK_TOP) ? top_smem + 4 * (size_t)(link & (RTW_LINK_TOP - 1))
                                                 : sc.nodes + 4 * (size_t)link;
         const float4 l0 = n[0], l1 = n[1], r0 = n[2], r1 = n[3];
+#elif RTW_TOP_TREE > 0
+        float4 l0, l1, r0, r1;
+        if (link & RTW_LINK_TOP) {  // LDS.128 x4
+          const float4* n = top_smem + 4 * (size_t)(link & (RTW_LINK_TOP - 1));
+          l0 = n[0]; l1 = n[1]; r0 = n[2]; r1 = n[3];
+        } else {  // LDG.128 x4 through the read-only path
+          const float4* __restrict__ n = sc.nodes + 4 * (size_t)link;
+          l0 = __ldg(n); l1 = __ldg(n + 1); r0 = __ldg(n + 2); r1 = __ldg(n + 3);
+        }
 #else
         const float4* __restrict__ n = sc.nodes + 4 * (size_t)link;
         const float4 l0 = __ldg(n), l1 = __ldg(n + 1), r0 = __ldg(n + 2), r1 = __ldg(n + 3);
