@@ -57,6 +57,9 @@ __device__ __forceinline__ bool slab(float4 lo, float4 hi, v3 o, v3 inv, float t
   return t_min <= t_far;
 }
 
+#ifndef RTW_RECT_PERM_CACHE
+#define RTW_RECT_PERM_CACHE 0
+#endif
 #ifndef RTW_TOP_TREE_GENERIC
 #define RTW_TOP_TREE_GENERIC 0
 #endif
@@ -290,6 +293,7 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
         const uint32_t slot = first + k;
         const uint32_t pm = __ldg(sc.slot_meta + slot);
         const uint32_t type = pm & 7u;
+#if RTW_RECT_PERM_CACHE
         if (pm != cur_pm) {
           const uint32_t inst = pm >> RTW_META_TYPE_BITS;
           if (inst != cur_inst) {
@@ -305,6 +309,16 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
           }
           cur_pm = pm;
         }
+#else
+        {
+          const uint32_t inst = pm >> RTW_META_TYPE_BITS;
+          if (inst != cur_inst) {
+            oi = o; di = d;
+            if (inst != 0) ray_to_instance(sc, inst, oi, di);
+            cur_inst = inst;
+          }
+        }
+#endif
         if (COUNT) {
           cnt.prims++;
           cnt.prim_bytes += 4u + ((type == PT_SPHERE) ? 16u : (((type >= PT_RECT_YZ && type <= PT_RECT_XY) || type >= PT_MEDIUM_SPHERE) ? 32u : 48u));
@@ -316,8 +330,21 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
           Rng rng;
           io.rng_key(rng);
           hit = medium_t(type, g, oi, di, d, t_min, best_t, rng.gen_f32_keyed((uint32_t)__ldg(sc.slot_prim + slot)), t);
-        } else if (type >= PT_RECT_YZ && type <= PT_RECT_XY)
+        }
+#if RTW_RECT_PERM_CACHE
+        else if (type >= PT_RECT_YZ && type <= PT_RECT_XY)
           hit = rect_t_perm(oA, oB, oK, dA, dB, dK, t_min, best_t, __ldg(g), __ldg(reinterpret_cast<const float*>(g + 1)), t);
+#else
+        // one straight-line path per orientation: the components are picked at compile time (no per-run
+        // permutation of the ray: 21 % of the instructions of the flat Cornell scene, profiles/r01_final), and in
+        // a flat scene the whole warp takes the same path
+        else if (type == PT_RECT_XZ)
+          hit = rect_t_perm(oi.x, oi.z, oi.y, di.x, di.z, di.y, t_min, best_t, __ldg(g), __ldg(reinterpret_cast<const float*>(g + 1)), t);
+        else if (type == PT_RECT_XY)
+          hit = rect_t_perm(oi.x, oi.y, oi.z, di.x, di.y, di.z, t_min, best_t, __ldg(g), __ldg(reinterpret_cast<const float*>(g + 1)), t);
+        else if (type == PT_RECT_YZ)
+          hit = rect_t_perm(oi.y, oi.z, oi.x, di.y, di.z, di.x, t_min, best_t, __ldg(g), __ldg(reinterpret_cast<const float*>(g + 1)), t);
+#endif
         else
           hit = prim_t(type, g, oi, di, time, t_min, best_t, t);
         if (hit) {
