@@ -167,7 +167,7 @@ def test_image_is_independent_of_pool_partition_and_counters(gpu):
         a, st = s.render(cam, s.params(w, h, spp, seed=9, slices=3, flags=rtw.RTW_RENDER_COUNT_TRAVERSAL | rtw.RTW_RENDER_TIME_KERNELS))
         assert np.array_equal(bits(a), bits(ref))
         assert st.node_visits > st.segments and st.prim_tests > 0 and st.prim_bytes > 0 and st.ms_traverse > 0
-        for parts, ts in ((2, 32), (3, 16), (8, 32)):
+        for parts, ts in ((2, 32), (3, 16), (8, 32), (5, 24)):   # 24: the non-power-of-two tile path
             total = np.zeros_like(ref)
             seg = 0
             for r in range(parts):
