@@ -340,6 +340,34 @@ __global__ void k_karras(int n, const uint64_t* __restrict__ keys, uint32_t* __r
   node_range[i] = make_uint2((uint32_t)lo, (uint32_t)(hi - lo + 1));
 }
 
+// Kernel: the 4-wide view of the tree.  Record i holds the children of pair i's two children (a child that is a
+// leaf stands for itself), i.e. the four boxes a ray meets two levels below pair i, in one 128-byte record: a
+// traversal step through it replaces two dependent pair fetches by one.  Unused entries: link = RTW_LINK_DONE
+// and an empty box.  Only pairs at even depth are ever visited through this view; building it for every pair
+// keeps the indices identical to the binary tree's.
+__global__ void k_build_wide(uint32_t num_nodes, const float4* __restrict__ nodes, float4* __restrict__ nodes4) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= num_nodes) return;
+  const float INF = __int_as_float(0x7f800000);
+  float4 out[8];
+  int n = 0;
+  for (int c = 0; c < 2; ++c) {
+    const float4 r0 = nodes[4 * (size_t)i + 2 * c], r1 = nodes[4 * (size_t)i + 2 * c + 1];
+    const int32_t link = __float_as_int(r0.w);
+    if (link >= 0) {
+      const float4* q = nodes + 4 * (size_t)link;
+      out[n++] = q[0]; out[n++] = q[1]; out[n++] = q[2]; out[n++] = q[3];
+    } else {
+      out[n++] = r0; out[n++] = r1;
+    }
+  }
+  for (; n < 8; n += 2) {
+    out[n] = make_float4(INF, INF, INF, __int_as_float((int32_t)0x80000000));
+    out[n + 1] = make_float4(-INF, -INF, -INF, 0.f);
+  }
+  for (int k = 0; k < 8; ++k) nodes4[8 * (size_t)i + k] = out[k];
+}
+
 // Kernel (one thread): the first `cap` pairs of the tree in breadth-first order, for the shared-memory top of
 // tree of the traversal kernels.  A child link that points to a pair inside the copy is re-targeted to its index
 // in the copy and tagged RTW_LINK_TOP; every other link (deeper pairs, leaves) is kept.
@@ -654,6 +682,12 @@ int build_scene_device(rtw_scene* s, float time0, float time1, rtw_build_stats* 
                     d_nodes, d_root, d_info);
   if (n > 1) k_sort_leaf_ranges<<<G, T>>>(n - 1, d_collapsed, d_nparent, d_nrange, d.prim_meta, d_v0);
   k_emit_leaves<<<G, T>>>(n, d_v0, d_enc, d.prim_meta, d.prim_mat, d.prim_shade, d_geom, d_slot_prim, d_slot_meta, d_slot_ms);
+  {
+    float4* d_nodes4;
+    if ((rc = dev_alloc(s, &d_nodes4, 8 * (size_t)d.num_nodes))) return rc;
+    k_build_wide<<<(d.num_nodes + T - 1) / T, T>>>(d.num_nodes, d_nodes, d_nodes4);
+    d.nodes4 = d_nodes4;
+  }
   d.top_nodes = nullptr;
   d.top_count = 0;
 #if RTW_TOP_TREE > 0

@@ -87,7 +87,7 @@ struct WaveHost {
   WaveCtl* pinned_ctl = nullptr;   // [RTW_MAX_SUBPOOLS][2]: ring for the lagging termination check
   cudaStream_t stream = nullptr;    // internal non-blocking stream (graph capture needs a non-legacy stream)
   cudaStream_t pool_stream[RTW_MAX_SUBPOOLS] = {};
-  int blocks_traverse = 0, blocks_traverse_count = 0, blocks_shade = 0;
+  int blocks_traverse = 0, blocks_traverse_wide = 0, blocks_traverse_count = 0, blocks_shade = 0;
 };
 
 // ---- work items ---------------------------------------------------------------------------------
@@ -259,14 +259,13 @@ struct WaveIO {
   }
 };
 
-template <bool COUNT, bool MEDIA>
 // 8 resident blocks (64 registers) for the product variant: A/B r01 +2..3 % over the compiler's own choice (72)
 #ifndef RTW_TRAVERSE_MINBLOCKS
 #define RTW_TRAVERSE_MINBLOCKS 8
 #endif
-__global__ void __launch_bounds__(128, (COUNT || MEDIA) ? 1 : RTW_TRAVERSE_MINBLOCKS) k_wave_traverse(
-    SceneDev sc, WaveDev w, uint32_t parity, uint32_t seed_lo,
-                                                       uint32_t seed_hi) {
+template <bool COUNT, bool MEDIA, bool WIDE>
+__global__ void __launch_bounds__(128, (COUNT || MEDIA || WIDE) ? 1 : RTW_TRAVERSE_MINBLOCKS)
+    k_wave_traverse(SceneDev sc, WaveDev w, uint32_t parity, uint32_t seed_lo, uint32_t seed_hi) {
   WaveCtl* ctl = w.ctl;
   const uint32_t count = ctl->count[parity];
   const uint32_t in_queue = ctl->qmode[parity];
@@ -284,9 +283,9 @@ __global__ void __launch_bounds__(128, (COUNT || MEDIA) ? 1 : RTW_TRAVERSE_MINBL
 #if RTW_TOP_TREE > 0
   __shared__ float4 top_smem[4 * RTW_TOP_TREE];
   stage_top_tree(sc, top_smem);
-  traverse_persistent<COUNT, MEDIA>(sc, io, count, &ctl->cursor_traverse, cnt, top_smem);
+  traverse_persistent<COUNT, MEDIA, WIDE>(sc, io, count, &ctl->cursor_traverse, cnt, top_smem);
 #else
-  traverse_persistent<COUNT, MEDIA>(sc, io, count, &ctl->cursor_traverse, cnt);
+  traverse_persistent<COUNT, MEDIA, WIDE>(sc, io, count, &ctl->cursor_traverse, cnt);
 #endif
   if (COUNT) {
     uint32_t p = cnt.pairs, q = cnt.prims, r = cnt.prim_bytes;
@@ -637,11 +636,13 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
     for (auto& ps : wh->pool_stream) RTW_CUDA_TRY(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
     int nb = 0;
     if (s->dev.has_media)
-      RTW_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wave_traverse<false, true>, 128, 0));
+      RTW_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wave_traverse<false, true, false>, 128, 0));
     else
-      RTW_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wave_traverse<false, false>, 128, 0));
+      RTW_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wave_traverse<false, false, false>, 128, 0));
     wh->blocks_traverse = std::max(nb, 1) * s->num_sms;
-    RTW_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wave_traverse<true, true>, 128, 0));
+    RTW_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wave_traverse<false, false, true>, 128, 0));
+    wh->blocks_traverse_wide = std::max(nb, 1) * s->num_sms;
+    RTW_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wave_traverse<true, true, false>, 128, 0));
     wh->blocks_traverse_count = std::max(nb, 1) * s->num_sms;
     RTW_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wave_shade, 128, 0));
     wh->blocks_shade = std::max(nb, 1) * s->num_sms;
@@ -666,6 +667,13 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
   }
   WaveDev& w = wh->dev;
 
+  // The 4-wide walk (SceneDev::nodes4) halves the dependent node fetches but moves MORE bytes (it fetches the boxes
+  // below a child whose own box the ray misses).  Measured r01: no gain on C5 (257 vs 253 ms) — that traversal sits at
+  // the random-gather bandwidth of the memory system (tools/gather_peak.cu: 1.3 TB/s beyond L2), not at its latency —
+  // and 5-17 % slower on cache-resident scenes.  Off unless RTW_WIDE=1 (parity-tested).
+  bool wide = false;
+  if (const char* e = getenv("RTW_WIDE"))
+    wide = atoi(e) != 0 && !s->dev.has_media && 3u * (s->bvh_height / 2u + 1u) + 2u <= RTW_STACK_SIZE;
   const bool count_trav = (p->flags & RTW_RENDER_COUNT_TRAVERSAL) != 0;
   const bool time_kernels = (p->flags & 2u) != 0;
   // All work runs on an internal stream ordered after the caller's stream; the call returns only after
@@ -714,7 +722,7 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
       // ---- product path: per sub-pool a CUDA graph of BATCH iterations, launched back to back; the host
       // looks at the live count of round i-1 while round i is already running.
       const int BATCH = 16;  // even: the queue parity is back to 0 after every batch
-      int grid_t = wh->blocks_traverse, grid_s = wh->blocks_shade;
+      int grid_t = wh->blocks_traverse, grid_s = wh->blocks_shade, grid_tw = wh->blocks_traverse_wide;
       if (const char* e = getenv("RTW_GRID_FRAC")) {  // experiment: leave room for the other sub-pool's kernel on every SM
         float fr = (float)atof(e);
         grid_t = std::max(s->num_sms, (int)(grid_t * fr));
@@ -735,9 +743,11 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
         RTW_CUDA_TRY(cudaStreamBeginCapture(sk, cudaStreamCaptureModeThreadLocal));
         for (int b = 0; b < BATCH; ++b) {
           if (s->dev.has_media)
-            k_wave_traverse<false, true><<<grid_t, 128, 0, sk>>>(s->dev, wk[k], (uint32_t)(b & 1), f.seed_lo, f.seed_hi);
+            k_wave_traverse<false, true, false><<<grid_t, 128, 0, sk>>>(s->dev, wk[k], (uint32_t)(b & 1), f.seed_lo, f.seed_hi);
+          else if (wide)
+            k_wave_traverse<false, false, true><<<grid_tw, 128, 0, sk>>>(s->dev, wk[k], (uint32_t)(b & 1), f.seed_lo, f.seed_hi);
           else
-            k_wave_traverse<false, false><<<grid_t, 128, 0, sk>>>(s->dev, wk[k], (uint32_t)(b & 1), f.seed_lo, f.seed_hi);
+            k_wave_traverse<false, false, false><<<grid_t, 128, 0, sk>>>(s->dev, wk[k], (uint32_t)(b & 1), f.seed_lo, f.seed_hi);
           k_wave_shade<<<grid_s, 128, 0, sk>>>(s->dev, f, wk[k], d_accum, (uint32_t)(b & 1));
         }
         RTW_CUDA_TRY(cudaStreamEndCapture(sk, &graph[k]));
@@ -789,11 +799,13 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
             RTW_CUDA_TRY(cudaEventRecord(e4[0], st));
           }
           if (count_trav)
-            k_wave_traverse<true, true><<<wh->blocks_traverse_count, 128, 0, st>>>(s->dev, wk[0], parity, f.seed_lo, f.seed_hi);
+            k_wave_traverse<true, true, false><<<wh->blocks_traverse_count, 128, 0, st>>>(s->dev, wk[0], parity, f.seed_lo, f.seed_hi);
           else if (s->dev.has_media)
-            k_wave_traverse<false, true><<<wh->blocks_traverse_count, 128, 0, st>>>(s->dev, wk[0], parity, f.seed_lo, f.seed_hi);
+            k_wave_traverse<false, true, false><<<wh->blocks_traverse_count, 128, 0, st>>>(s->dev, wk[0], parity, f.seed_lo, f.seed_hi);
+          else if (wide)
+            k_wave_traverse<false, false, true><<<wh->blocks_traverse_wide, 128, 0, st>>>(s->dev, wk[0], parity, f.seed_lo, f.seed_hi);
           else
-            k_wave_traverse<false, false><<<wh->blocks_traverse, 128, 0, st>>>(s->dev, wk[0], parity, f.seed_lo, f.seed_hi);
+            k_wave_traverse<false, false, false><<<wh->blocks_traverse, 128, 0, st>>>(s->dev, wk[0], parity, f.seed_lo, f.seed_hi);
           if (time_kernels) {
             RTW_CUDA_TRY(cudaEventRecord(kev[kev.size() - 3], st));
             RTW_CUDA_TRY(cudaEventRecord(kev[kev.size() - 2], st));

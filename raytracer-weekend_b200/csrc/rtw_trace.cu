@@ -1,6 +1,7 @@
 // rtw_trace_closest: closest hit of a ray batch — the parity entry point.
 // One thread per ray; AoS rtw_ray in, AoS rtw_hit out (the full HitRecord of hittable/mod.rs:22-29).
 #include <algorithm>
+#include <cstdlib>
 
 #include "rtw_scene.cuh"
 #include "rtw_traverse.cuh"
@@ -51,7 +52,7 @@ struct BatchIO {
 };
 
 // the product path: the same persistent traversal the wavefront renderer runs
-template <bool MEDIA>
+template <bool MEDIA, bool WIDE>
 __global__ void __launch_bounds__(128) k_trace_bvh(SceneDev sc, const rtw_ray* __restrict__ rays, uint32_t n,
                                                    rtw_hit* __restrict__ hits, uint32_t* cursor) {
   BatchIO io{sc, rays, hits};
@@ -59,9 +60,9 @@ __global__ void __launch_bounds__(128) k_trace_bvh(SceneDev sc, const rtw_ray* _
 #if RTW_TOP_TREE > 0
   __shared__ float4 top_smem[4 * RTW_TOP_TREE];
   stage_top_tree(sc, top_smem);
-  traverse_persistent<false, MEDIA>(sc, io, n, cursor, cnt, top_smem);
+  traverse_persistent<false, MEDIA, WIDE>(sc, io, n, cursor, cnt, top_smem);
 #else
-  traverse_persistent<false, MEDIA>(sc, io, n, cursor, cnt);
+  traverse_persistent<false, MEDIA, WIDE>(sc, io, n, cursor, cnt);
 #endif
 }
 
@@ -90,9 +91,13 @@ int trace_closest_device(rtw_scene* s, const rtw_ray* d_rays, uint64_t n, rtw_hi
     // persistent grid; batches above 2^31 rays are split
     static thread_local int blocks_per_sm = 0;
     if (!blocks_per_sm) {
-      RTW_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_trace_bvh<true>, (int)T, 0));
+      RTW_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_trace_bvh<true, false>, (int)T, 0));
       blocks_per_sm = blocks_per_sm > 0 ? blocks_per_sm : 1;
     }
+    // same switch as the renderer (rtw_render.cu): the 4-wide walk is an experiment, off unless RTW_WIDE=1
+    bool wide = false;
+    if (const char* e = getenv("RTW_WIDE"))
+      wide = atoi(e) != 0 && !s->dev.has_media && 3u * (s->bvh_height / 2u + 1u) + 2u <= RTW_STACK_SIZE;
     uint32_t* cursor = nullptr;
     RTW_CUDA_TRY(cudaMallocAsync((void**)&cursor, sizeof(uint32_t), st));
     for (uint64_t done = 0; done < n;) {
@@ -100,9 +105,11 @@ int trace_closest_device(rtw_scene* s, const rtw_ray* d_rays, uint64_t n, rtw_hi
       RTW_CUDA_TRY(cudaMemsetAsync(cursor, 0, sizeof(uint32_t), st));
       uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)blocks_per_sm * s->num_sms, (chunk + T - 1) / T);
       if (s->dev.has_media)
-        k_trace_bvh<true><<<grid, T, 0, st>>>(s->dev, d_rays + done, chunk, d_hits + done, cursor);
+        k_trace_bvh<true, false><<<grid, T, 0, st>>>(s->dev, d_rays + done, chunk, d_hits + done, cursor);
+      else if (wide)
+        k_trace_bvh<false, true><<<grid, T, 0, st>>>(s->dev, d_rays + done, chunk, d_hits + done, cursor);
       else
-        k_trace_bvh<false><<<grid, T, 0, st>>>(s->dev, d_rays + done, chunk, d_hits + done, cursor);
+        k_trace_bvh<false, false><<<grid, T, 0, st>>>(s->dev, d_rays + done, chunk, d_hits + done, cursor);
       done += chunk;
     }
     RTW_CUDA_TRY(cudaFreeAsync(cursor, st));

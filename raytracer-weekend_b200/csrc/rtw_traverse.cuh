@@ -20,18 +20,34 @@
 namespace rtw {
 
 #define RTW_LINK_DONE ((int32_t)0x80000000)  // ~slot never reaches it (slot < 2^28)
-#ifndef RTW_SPECULATE
-#define RTW_SPECULATE 0  // A/B r01 (profiles/r01_sweeps.txt): the vote alone wins; postponing costs 8 registers and wasted steps
+
+// ---- tuning switches.  The defaults are the measured best on B200; every alternative was A/B-tested on the same
+// box and is kept compiled out for the record (numbers: profiles/r01_sweeps.txt).
+#ifndef RTW_REFILL_IDLE
+#define RTW_REFILL_IDLE 12      // refill once this many lanes of the warp are idle (1 / 4 / 8 / 12 within 2 %)
 #endif
 #ifndef RTW_NODE_EXIT_LANES
-#define RTW_NODE_EXIT_LANES 8
+#define RTW_NODE_EXIT_LANES 8   // the node phase ends when fewer lanes than this still walk and a leaf waits (0 = never)
+#endif
+#ifndef RTW_SPECULATE
+#define RTW_SPECULATE 0         // postpone the first leaf and keep walking (Aila-Laine): +8 registers, slower
 #endif
 #ifndef RTW_LEAF_PHASE_DRAIN
-#define RTW_LEAF_PHASE_DRAIN 0
+#define RTW_LEAF_PHASE_DRAIN 0  // leaf phase tests every leaf a lane pops, not at most two: no gain
 #endif
-#ifndef RTW_REFILL_IDLE
-#define RTW_REFILL_IDLE 12  // refill once this many lanes of the warp are idle (A/B r01: 1 / 4 / 8 / 12 within 2 %, 12 best)
+#ifndef RTW_RECT_PERM_CACHE
+#define RTW_RECT_PERM_CACHE 0   // permute the ray per rectangle run instead of one code path per orientation: slower
 #endif
+#ifndef RTW_CURSOR_CHUNKS
+#define RTW_CURSOR_CHUNKS 0     // private 32-entry chunks with a prefetched cursor: 3-13 % slower
+#endif
+#ifndef RTW_PREFETCH_FAR
+#define RTW_PREFETCH_FAR 0      // prefetch.global.L2 of the postponed child: 3-8 % slower
+#endif
+#ifndef RTW_TOP_TREE_GENERIC
+#define RTW_TOP_TREE_GENERIC 0  // RTW_TOP_TREE > 0 only: generic loads instead of an LDS / LDG branch
+#endif
+// RTW_TOP_TREE (rtw_device.cuh): shared-memory copy of the top of the tree — 5-14 % slower, default 0.
 
 // Slab test of one child record against the ray: aabb.rs:23-48 with (a) the reciprocal hoisted out
 // of the node loop (1/d is the same value every time), (b) a NON-strict reject (the reference
@@ -57,18 +73,6 @@ __device__ __forceinline__ bool slab(float4 lo, float4 hi, v3 o, v3 inv, float t
   return t_min <= t_far;
 }
 
-#ifndef RTW_RECT_PERM_CACHE
-#define RTW_RECT_PERM_CACHE 0
-#endif
-#ifndef RTW_TOP_TREE_GENERIC
-#define RTW_TOP_TREE_GENERIC 0
-#endif
-#ifndef RTW_CURSOR_CHUNKS
-#define RTW_CURSOR_CHUNKS 0  // A/B r01: private 32-entry chunks with a prefetched cursor are 3-13 % SLOWER (partial refills, drain imbalance)
-#endif
-#ifndef RTW_PREFETCH_FAR
-#define RTW_PREFETCH_FAR 0
-#endif
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 struct TraverseCounters {
@@ -77,22 +81,6 @@ struct TraverseCounters {
   uint32_t prim_bytes = 0;
 };
 
-// Drain cut-off (IO::kSuspendLanes > 0): once the cursor has run dry a warp only drains what it holds, and a
-// launch ends with every SM waiting for a handful of long rays (measured: 67 us of a 260 us launch on the cow
-// scene, profiles/r01_sweeps.txt).  A warp left with <= kSuspendLanes rays therefore SUSPENDS them: the closest
-// hit found so far is published with a "pending" mark, the next launch restarts the ray with that hit as its
-// t_max (the result of a closest-hit query does not depend on how it is split — same tie rule), and the shade
-// kernel leaves pending slots alone.  A restarted ray is never suspended again, so every ray finishes within
-// two launches.
-//
-// IO policy of traverse_persistent:
-//   bool load(uint32_t index, v3& o, v3& d, float& time, float& t_min, float& t_max, int32_t& slot0, bool& resumed)
-//        fetch ray `index`; slot0 >= 0 / resumed: the ray was suspended with the hit (slot0, t_max)
-//   void suspend(uint32_t index, int32_t slot, float t)   publish the closest hit so far, mark the ray pending
-//   void store(uint32_t index, v3 o, v3 d, float time, int32_t slot, float t, uint32_t meta)   publish its closest hit
-//   void rng_key(Rng& rng)   (pixel, sample, stage, seed) of the current ray — only called when a medium is tested
-// MEDIA = the scene contains ConstantMedium primitives (compiled out otherwise: the keyed draw and the
-// boundary tests cost registers and branches in the hottest loop).
 // Stage the top of the tree (rtw_bvh.cu: k_top_tree) in shared memory; call with the whole block.
 __device__ __forceinline__ void stage_top_tree(const SceneDev& sc, float4* top_smem) {
 #if RTW_TOP_TREE > 0
@@ -101,7 +89,26 @@ __device__ __forceinline__ void stage_top_tree(const SceneDev& sc, float4* top_s
 #endif
 }
 
-template <bool COUNT, bool MEDIA, class IO>
+// IO policy of traverse_persistent:
+//   bool load(uint32_t index, v3& o, v3& d, float& time, float& t_min, float& t_max, int32_t& slot0, bool& resumed)
+//        fetch ray `index`; slot0 >= 0 / resumed: the ray was suspended with the hit (slot0, t_max)
+//   void store(uint32_t index, v3 o, v3 d, float time, int32_t slot, float t, uint32_t meta)   publish its closest hit
+//   void suspend(uint32_t index, int32_t slot, float t)   publish the closest hit so far, mark the ray pending
+//   void rng_key(Rng& rng)   (pixel, sample, stage, seed) of the current ray — only called when a medium is tested
+//   static constexpr int kSuspendLanes   drain cut-off, see below (0 = off, the default)
+// MEDIA = the scene contains ConstantMedium primitives (compiled out otherwise: the keyed draw and the
+// boundary tests cost registers and branches in the hottest loop).
+//
+// Drain cut-off (IO::kSuspendLanes > 0, measured slower and off by default): once the cursor has run dry a warp
+// only drains what it holds, and a launch ends with every SM waiting for a handful of long rays (67 us of a 260 us
+// launch on the cow scene).  A warp left with <= kSuspendLanes rays SUSPENDS them: the closest hit found so far is
+// published with a "pending" mark, the next launch restarts the ray with that hit as its t_max (the result of a
+// closest-hit query does not depend on how it is split — same tie rule), and the shade kernel leaves pending
+// slots alone.  A restarted ray is never suspended again, so every ray finishes within two launches.
+// WIDE = walk the 4-wide view (SceneDev::nodes4): one 128-byte record and four slab tests per step, half the
+// dependent fetches of the pair walk — for hierarchies that do not fit the caches, where a step costs a DRAM
+// round trip (config C5).
+template <bool COUNT, bool MEDIA, bool WIDE = false, class IO>
 __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, uint32_t count, uint32_t* cursor,
                                                     TraverseCounters& cnt, const float4* top_smem = nullptr) {
   const uint32_t lane = threadIdx.x & 31;
@@ -210,7 +217,47 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
           __any_sync(0xffffffffu, active && (pl_meta != 0u || (link < 0 && link != RTW_LINK_DONE))))
         break;
 #endif
-      if (searching) {
+      if (WIDE && searching) {
+        const float4* __restrict__ n = sc.nodes4 + 8 * (size_t)link;
+        if (COUNT) cnt.pairs += 2;
+        const float INF = __int_as_float(0x7f800000);
+        float tk[4];
+        int32_t lk[4];
+        uint32_t mk4[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 lo = __ldg(n + 2 * c), hi = __ldg(n + 2 * c + 1);
+          float t;
+          const int32_t l = __float_as_int(lo.w);
+          const bool h = (l != RTW_LINK_DONE) && slab(lo, hi, o, inv, t_min, best_t, t);
+          lk[c] = h ? l : RTW_LINK_DONE;
+          tk[c] = h ? t : INF;
+          mk4[c] = __float_as_uint(hi.w);
+        }
+        // sort the four by entry distance (misses sort last): 5-comparator network
+#define RTW_CSWAP(a, b)                                                  \
+  {                                                                      \
+    const bool sw = tk[b] < tk[a];                                       \
+    const float tt = sw ? tk[a] : tk[b]; tk[a] = sw ? tk[b] : tk[a]; tk[b] = tt;          \
+    const int32_t ll = sw ? lk[a] : lk[b]; lk[a] = sw ? lk[b] : lk[a]; lk[b] = ll;        \
+    const uint32_t mm = sw ? mk4[a] : mk4[b]; mk4[a] = sw ? mk4[b] : mk4[a]; mk4[b] = mm; \
+  }
+        RTW_CSWAP(0, 1) RTW_CSWAP(2, 3) RTW_CSWAP(0, 2) RTW_CSWAP(1, 3) RTW_CSWAP(1, 2)
+#undef RTW_CSWAP
+        // hits form a prefix; the farthest is pushed first so that the nearest of the rest is popped first
+        if (lk[3] != RTW_LINK_DONE) stack[sp++] = make_int2(lk[3], (int)mk4[3]);
+        if (lk[2] != RTW_LINK_DONE) stack[sp++] = make_int2(lk[2], (int)mk4[2]);
+        if (lk[1] != RTW_LINK_DONE) stack[sp++] = make_int2(lk[1], (int)mk4[1]);
+        if (lk[0] != RTW_LINK_DONE) {
+          link = lk[0]; meta = mk4[0];
+        } else if (sp > 0) {
+          const int2 e = stack[--sp];
+          link = e.x; meta = (uint32_t)e.y;
+        } else {
+          link = RTW_LINK_DONE;
+        }
+      }
+      if (!WIDE && searching) {
 #if RTW_TOP_TREE > 0 && RTW_TOP_TREE_GENERIC
         // generic loads: the pair lies in shared memory (top of the tree) or in global memory
         const float4* n = (link & RTW_LINK_TOP) ? top_smem + 4 * (size_t)(link & (RTW_LINK_TOP - 1))
