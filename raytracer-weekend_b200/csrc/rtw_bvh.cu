@@ -10,6 +10,7 @@
 // are then padded by 2^-20 of the scene's largest coordinate: the traversal tests primitives in
 // OBJECT space with a transformed ray whose rounding differs from the world-space slab test.
 #include <algorithm>
+#include <cmath>
 #include <cfloat>
 #include <cstdio>
 #include <cstdlib>
@@ -338,6 +339,56 @@ __global__ void k_karras(int n, const uint64_t* __restrict__ keys, uint32_t* __r
   if (hi == gamma + 1) leaf_parent[gamma + 1] = me | 1u; else node_parent[gamma + 1] = me | 1u;
   if (i == 0) node_parent[0] = 0xFFFFFFFFu;
   node_range[i] = make_uint2((uint32_t)lo, (uint32_t)(hi - lo + 1));
+}
+
+// Kernel: compact pairs for hierarchies that do not fit the caches.  Beyond L2 a child-pair fetch is a random
+// 64-byte gather, and HBM serves those at ~1.3 TB/s whatever the parallelism (tools/gather_peak.cu): the only way to
+// go faster is to move fewer bytes.  A compact pair is 32 bytes: both child boxes as 16-bit coordinates on a uniform
+// grid over the scene's root box (lo rounded down, hi rounded up, checked with the traversal's own dequantisation
+// expression, so the compact box always CONTAINS the exact one: culling stays conservative), plus one word per
+// child: an internal link (pair index) or 0x80000000 | (count - 1) << 26 | first slot for a leaf.
+struct QuantGrid {
+  float lo[3], step[3];
+};
+__device__ __forceinline__ uint32_t quant_down(float x, float lo, float step) {
+  float q = floorf((x - lo) / step);
+  q = fminf(fmaxf(q, 0.0f), 65535.0f);
+  while (q > 0.0f && __fmaf_rn(q, step, lo) > x) q -= 1.0f;
+  return (uint32_t)q;
+}
+__device__ __forceinline__ uint32_t quant_up(float x, float lo, float step) {
+  float q = ceilf((x - lo) / step);
+  q = fminf(fmaxf(q, 0.0f), 65535.0f);
+  while (q < 65535.0f && __fmaf_rn(q, step, lo) < x) q += 1.0f;
+  return (uint32_t)q;
+}
+__global__ void k_build_compact(uint32_t num_nodes, const float4* __restrict__ nodes, QuantGrid g, uint4* __restrict__ out,
+                                uint32_t* __restrict__ bad) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= num_nodes) return;
+  for (int c = 0; c < 2; ++c) {
+    const float4 lo = nodes[4 * (size_t)i + 2 * c], hi = nodes[4 * (size_t)i + 2 * c + 1];
+    const uint32_t lx = quant_down(lo.x, g.lo[0], g.step[0]), ly = quant_down(lo.y, g.lo[1], g.step[1]),
+                   lz = quant_down(lo.z, g.lo[2], g.step[2]);
+    const uint32_t hx = quant_up(hi.x, g.lo[0], g.step[0]), hy = quant_up(hi.y, g.lo[1], g.step[1]),
+                   hz = quant_up(hi.z, g.lo[2], g.step[2]);
+    // containment must hold exactly (a coordinate outside the grid, a NaN box): otherwise the scene keeps the fp32 pairs
+    if (!(__fmaf_rn((float)lx, g.step[0], g.lo[0]) <= lo.x && __fmaf_rn((float)ly, g.step[1], g.lo[1]) <= lo.y &&
+          __fmaf_rn((float)lz, g.step[2], g.lo[2]) <= lo.z && __fmaf_rn((float)hx, g.step[0], g.lo[0]) >= hi.x &&
+          __fmaf_rn((float)hy, g.step[1], g.lo[1]) >= hi.y && __fmaf_rn((float)hz, g.step[2], g.lo[2]) >= hi.z))
+      atomicExch(bad, 1u);
+    const int32_t link = __float_as_int(lo.w);
+    const uint32_t meta = __float_as_uint(hi.w);
+    uint32_t w;
+    if (link >= 0) {
+      w = (uint32_t)link;
+    } else {
+      const uint32_t first = (uint32_t)(~link);
+      if (link == (int32_t)0x80000000 || first >= (1u << 26) || meta == 0u || meta > 32u) atomicExch(bad, 1u);
+      w = 0x80000000u | ((meta - 1u) << 26) | (first & 0x3FFFFFFu);
+    }
+    out[2 * (size_t)i + c] = make_uint4(lx | (ly << 16), lz | (hx << 16), hy | (hz << 16), w);
+  }
 }
 
 // Kernel: the 4-wide view of the tree.  Record i holds the children of pair i's two children (a child that is a
@@ -710,6 +761,38 @@ int build_scene_device(rtw_scene* s, float time0, float time1, rtw_build_stats* 
   memcpy(s->root_box, h_root, 6 * sizeof(float));
   memcpy(&s->bvh_height, &h_root[6], 4);
   for (void* p : scratch) cudaFree(p);
+
+  // compact pairs: only worth their decode instructions when the hierarchy lives in HBM (>= 2^20 primitives)
+  d.nodes_c = nullptr;
+  {
+    bool want = n >= (1u << 20);
+    if (const char* e = getenv("RTW_COMPACT")) want = atoi(e) != 0;
+    if (want && n > 1 && n < (1u << 26)) {
+      QuantGrid g;
+      bool ok = true;
+      for (int a = 0; a < 3; ++a) {
+        const float lo = h_root[a], hi = h_root[3 + a];
+        g.lo[a] = lo;
+        g.step[a] = (hi > lo) ? (hi - lo) / 65535.0f * 1.000001f : 1.0f;
+        ok = ok && std::isfinite(lo) && std::isfinite(hi) && std::isfinite(g.step[a]) && g.step[a] > 0.0f &&
+             std::fma(65535.0f, g.step[a], lo) >= hi;
+      }
+      if (ok) {
+        uint4* d_nc;
+        uint32_t* d_bad;
+        if ((rc = dev_alloc(s, &d_nc, 2 * (size_t)d.num_nodes))) return rc;
+        if ((rc = dev_alloc(s, &d_bad, 1))) return rc;
+        RTW_CUDA_TRY(cudaMemset(d_bad, 0, sizeof(uint32_t)));
+        k_build_compact<<<(d.num_nodes + T - 1) / T, T>>>(d.num_nodes, d_nodes, g, d_nc, d_bad);
+        uint32_t bad = 1;
+        RTW_CUDA_TRY(cudaMemcpy(&bad, d_bad, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        if (!bad) {
+          d.nodes_c = d_nc;
+          for (int a = 0; a < 3; ++a) { d.grid_lo[a] = g.lo[a]; d.grid_step[a] = g.step[a]; }
+        }
+      }
+    }
+  }
 
   d.nodes = d_nodes;
   d.geom = d_geom;

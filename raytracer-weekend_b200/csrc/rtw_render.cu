@@ -79,6 +79,9 @@ struct FrameDev {
   uint32_t tile_shift;  // log2(tile_size) when it is a power of two, else 0xffffffff
 };
 
+// the traversal kernel variants a render can launch
+enum TravKind { TK_PAIR = 0, TK_MEDIA, TK_WIDE, TK_COMPACT, TK_COUNT, TK_COUNT_COMPACT, TK_N };
+
 struct WaveHost {
   WaveDev dev{};
   std::vector<void*> allocs;
@@ -87,7 +90,8 @@ struct WaveHost {
   WaveCtl* pinned_ctl = nullptr;   // [RTW_MAX_SUBPOOLS][2]: ring for the lagging termination check
   cudaStream_t stream = nullptr;    // internal non-blocking stream (graph capture needs a non-legacy stream)
   cudaStream_t pool_stream[RTW_MAX_SUBPOOLS] = {};
-  int blocks_traverse = 0, blocks_traverse_wide = 0, blocks_traverse_count = 0, blocks_shade = 0;
+  int blocks_trav[6] = {0, 0, 0, 0, 0, 0};  // persistent grid per TravKind
+  int blocks_shade = 0;
 };
 
 // ---- work items ---------------------------------------------------------------------------------
@@ -263,8 +267,8 @@ struct WaveIO {
 #ifndef RTW_TRAVERSE_MINBLOCKS
 #define RTW_TRAVERSE_MINBLOCKS 8
 #endif
-template <bool COUNT, bool MEDIA, bool WIDE>
-__global__ void __launch_bounds__(128, (COUNT || MEDIA || WIDE) ? 1 : RTW_TRAVERSE_MINBLOCKS)
+template <bool COUNT, bool MEDIA, int NODES>
+__global__ void __launch_bounds__(128, (COUNT || MEDIA || NODES == NODES_WIDE) ? 1 : RTW_TRAVERSE_MINBLOCKS)
     k_wave_traverse(SceneDev sc, WaveDev w, uint32_t parity, uint32_t seed_lo, uint32_t seed_hi) {
   WaveCtl* ctl = w.ctl;
   const uint32_t count = ctl->count[parity];
@@ -283,9 +287,9 @@ __global__ void __launch_bounds__(128, (COUNT || MEDIA || WIDE) ? 1 : RTW_TRAVER
 #if RTW_TOP_TREE > 0
   __shared__ float4 top_smem[4 * RTW_TOP_TREE];
   stage_top_tree(sc, top_smem);
-  traverse_persistent<COUNT, MEDIA, WIDE>(sc, io, count, &ctl->cursor_traverse, cnt, top_smem);
+  traverse_persistent<COUNT, MEDIA, NODES>(sc, io, count, &ctl->cursor_traverse, cnt, top_smem);
 #else
-  traverse_persistent<COUNT, MEDIA, WIDE>(sc, io, count, &ctl->cursor_traverse, cnt);
+  traverse_persistent<COUNT, MEDIA, NODES>(sc, io, count, &ctl->cursor_traverse, cnt);
 #endif
   if (COUNT) {
     uint32_t p = cnt.pairs, q = cnt.prims, r = cnt.prim_bytes;
@@ -635,15 +639,13 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
     RTW_CUDA_TRY(cudaStreamCreateWithFlags(&wh->stream, cudaStreamNonBlocking));
     for (auto& ps : wh->pool_stream) RTW_CUDA_TRY(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
     int nb = 0;
-    if (s->dev.has_media)
-      RTW_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wave_traverse<false, true, false>, 128, 0));
-    else
-      RTW_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wave_traverse<false, false, false>, 128, 0));
-    wh->blocks_traverse = std::max(nb, 1) * s->num_sms;
-    RTW_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wave_traverse<false, false, true>, 128, 0));
-    wh->blocks_traverse_wide = std::max(nb, 1) * s->num_sms;
-    RTW_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wave_traverse<true, true, false>, 128, 0));
-    wh->blocks_traverse_count = std::max(nb, 1) * s->num_sms;
+    const void* kernels[TK_N] = {(const void*)k_wave_traverse<false, false, NODES_PAIR>, (const void*)k_wave_traverse<false, true, NODES_PAIR>,
+                                 (const void*)k_wave_traverse<false, false, NODES_WIDE>, (const void*)k_wave_traverse<false, false, NODES_COMPACT>,
+                                 (const void*)k_wave_traverse<true, true, NODES_PAIR>, (const void*)k_wave_traverse<true, true, NODES_COMPACT>};
+    for (int k = 0; k < TK_N; ++k) {
+      RTW_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernels[k], 128, 0));
+      wh->blocks_trav[k] = std::max(nb, 1) * s->num_sms;
+    }
     RTW_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wave_shade, 128, 0));
     wh->blocks_shade = std::max(nb, 1) * s->num_sms;
   }
@@ -676,6 +678,20 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
     wide = atoi(e) != 0 && !s->dev.has_media && 3u * (s->bvh_height / 2u + 1u) + 2u <= RTW_STACK_SIZE;
   const bool count_trav = (p->flags & RTW_RENDER_COUNT_TRAVERSAL) != 0;
   const bool time_kernels = (p->flags & 2u) != 0;
+  // compact pairs exist only when rtw_build found the hierarchy too large for the caches (rtw_bvh.cu)
+  const bool compact = s->dev.nodes_c != nullptr && !s->dev.has_media;
+  const TravKind kind = count_trav ? (compact ? TK_COUNT_COMPACT : TK_COUNT)
+                                   : (s->dev.has_media ? TK_MEDIA : (compact ? TK_COMPACT : (wide ? TK_WIDE : TK_PAIR)));
+  auto launch_traverse = [&](cudaStream_t sk, const WaveDev& wd, uint32_t parity, int grid) {
+    switch (kind) {
+      case TK_PAIR: k_wave_traverse<false, false, NODES_PAIR><<<grid, 128, 0, sk>>>(s->dev, wd, parity, f.seed_lo, f.seed_hi); break;
+      case TK_MEDIA: k_wave_traverse<false, true, NODES_PAIR><<<grid, 128, 0, sk>>>(s->dev, wd, parity, f.seed_lo, f.seed_hi); break;
+      case TK_WIDE: k_wave_traverse<false, false, NODES_WIDE><<<grid, 128, 0, sk>>>(s->dev, wd, parity, f.seed_lo, f.seed_hi); break;
+      case TK_COMPACT: k_wave_traverse<false, false, NODES_COMPACT><<<grid, 128, 0, sk>>>(s->dev, wd, parity, f.seed_lo, f.seed_hi); break;
+      case TK_COUNT: k_wave_traverse<true, true, NODES_PAIR><<<grid, 128, 0, sk>>>(s->dev, wd, parity, f.seed_lo, f.seed_hi); break;
+      default: k_wave_traverse<true, true, NODES_COMPACT><<<grid, 128, 0, sk>>>(s->dev, wd, parity, f.seed_lo, f.seed_hi); break;
+    }
+  };
   // All work runs on an internal stream ordered after the caller's stream; the call returns only after
   // that stream has drained, so the caller's stream order is preserved on both sides.
   cudaStream_t user_stream = st;
@@ -722,12 +738,8 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
       // ---- product path: per sub-pool a CUDA graph of BATCH iterations, launched back to back; the host
       // looks at the live count of round i-1 while round i is already running.
       const int BATCH = 16;  // even: the queue parity is back to 0 after every batch
-      int grid_t = wh->blocks_traverse, grid_s = wh->blocks_shade, grid_tw = wh->blocks_traverse_wide;
-      if (const char* e = getenv("RTW_GRID_FRAC")) {  // experiment: leave room for the other sub-pool's kernel on every SM
-        float fr = (float)atof(e);
-        grid_t = std::max(s->num_sms, (int)(grid_t * fr));
-        grid_s = std::max(s->num_sms, (int)(grid_s * fr));
-      }
+      int grid_t = wh->blocks_trav[kind], grid_s = wh->blocks_shade;
+  
       cudaEvent_t ev_fork, ev_join[RTW_MAX_SUBPOOLS], ring_ev[RTW_MAX_SUBPOOLS][2];
       cudaGraph_t graph[RTW_MAX_SUBPOOLS];
       cudaGraphExec_t exec[RTW_MAX_SUBPOOLS];
@@ -742,12 +754,7 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
         launches++;
         RTW_CUDA_TRY(cudaStreamBeginCapture(sk, cudaStreamCaptureModeThreadLocal));
         for (int b = 0; b < BATCH; ++b) {
-          if (s->dev.has_media)
-            k_wave_traverse<false, true, false><<<grid_t, 128, 0, sk>>>(s->dev, wk[k], (uint32_t)(b & 1), f.seed_lo, f.seed_hi);
-          else if (wide)
-            k_wave_traverse<false, false, true><<<grid_tw, 128, 0, sk>>>(s->dev, wk[k], (uint32_t)(b & 1), f.seed_lo, f.seed_hi);
-          else
-            k_wave_traverse<false, false, false><<<grid_t, 128, 0, sk>>>(s->dev, wk[k], (uint32_t)(b & 1), f.seed_lo, f.seed_hi);
+          launch_traverse(sk, wk[k], (uint32_t)(b & 1), grid_t);
           k_wave_shade<<<grid_s, 128, 0, sk>>>(s->dev, f, wk[k], d_accum, (uint32_t)(b & 1));
         }
         RTW_CUDA_TRY(cudaStreamEndCapture(sk, &graph[k]));
@@ -798,14 +805,7 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
             for (auto& e : e4) { RTW_CUDA_TRY(cudaEventCreate(&e)); kev.push_back(e); }
             RTW_CUDA_TRY(cudaEventRecord(e4[0], st));
           }
-          if (count_trav)
-            k_wave_traverse<true, true, false><<<wh->blocks_traverse_count, 128, 0, st>>>(s->dev, wk[0], parity, f.seed_lo, f.seed_hi);
-          else if (s->dev.has_media)
-            k_wave_traverse<false, true, false><<<wh->blocks_traverse_count, 128, 0, st>>>(s->dev, wk[0], parity, f.seed_lo, f.seed_hi);
-          else if (wide)
-            k_wave_traverse<false, false, true><<<wh->blocks_traverse_wide, 128, 0, st>>>(s->dev, wk[0], parity, f.seed_lo, f.seed_hi);
-          else
-            k_wave_traverse<false, false, false><<<wh->blocks_traverse, 128, 0, st>>>(s->dev, wk[0], parity, f.seed_lo, f.seed_hi);
+          launch_traverse(st, wk[0], parity, wh->blocks_trav[kind]);
           if (time_kernels) {
             RTW_CUDA_TRY(cudaEventRecord(kev[kev.size() - 3], st));
             RTW_CUDA_TRY(cudaEventRecord(kev[kev.size() - 2], st));

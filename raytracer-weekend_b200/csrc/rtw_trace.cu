@@ -52,7 +52,7 @@ struct BatchIO {
 };
 
 // the product path: the same persistent traversal the wavefront renderer runs
-template <bool MEDIA, bool WIDE>
+template <bool MEDIA, int NODES>
 __global__ void __launch_bounds__(128) k_trace_bvh(SceneDev sc, const rtw_ray* __restrict__ rays, uint32_t n,
                                                    rtw_hit* __restrict__ hits, uint32_t* cursor) {
   BatchIO io{sc, rays, hits};
@@ -60,9 +60,9 @@ __global__ void __launch_bounds__(128) k_trace_bvh(SceneDev sc, const rtw_ray* _
 #if RTW_TOP_TREE > 0
   __shared__ float4 top_smem[4 * RTW_TOP_TREE];
   stage_top_tree(sc, top_smem);
-  traverse_persistent<false, MEDIA, WIDE>(sc, io, n, cursor, cnt, top_smem);
+  traverse_persistent<false, MEDIA, NODES>(sc, io, n, cursor, cnt, top_smem);
 #else
-  traverse_persistent<false, MEDIA, WIDE>(sc, io, n, cursor, cnt);
+  traverse_persistent<false, MEDIA, NODES>(sc, io, n, cursor, cnt);
 #endif
 }
 
@@ -91,7 +91,7 @@ int trace_closest_device(rtw_scene* s, const rtw_ray* d_rays, uint64_t n, rtw_hi
     // persistent grid; batches above 2^31 rays are split
     static thread_local int blocks_per_sm = 0;
     if (!blocks_per_sm) {
-      RTW_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_trace_bvh<true, false>, (int)T, 0));
+      RTW_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_trace_bvh<true, NODES_PAIR>, (int)T, 0));
       blocks_per_sm = blocks_per_sm > 0 ? blocks_per_sm : 1;
     }
     // same switch as the renderer (rtw_render.cu): the 4-wide walk is an experiment, off unless RTW_WIDE=1
@@ -105,11 +105,13 @@ int trace_closest_device(rtw_scene* s, const rtw_ray* d_rays, uint64_t n, rtw_hi
       RTW_CUDA_TRY(cudaMemsetAsync(cursor, 0, sizeof(uint32_t), st));
       uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)blocks_per_sm * s->num_sms, (chunk + T - 1) / T);
       if (s->dev.has_media)
-        k_trace_bvh<true, false><<<grid, T, 0, st>>>(s->dev, d_rays + done, chunk, d_hits + done, cursor);
+        k_trace_bvh<true, NODES_PAIR><<<grid, T, 0, st>>>(s->dev, d_rays + done, chunk, d_hits + done, cursor);
+      else if (s->dev.nodes_c)  // hierarchy beyond the caches: compact pairs (rtw_bvh.cu)
+        k_trace_bvh<false, NODES_COMPACT><<<grid, T, 0, st>>>(s->dev, d_rays + done, chunk, d_hits + done, cursor);
       else if (wide)
-        k_trace_bvh<false, true><<<grid, T, 0, st>>>(s->dev, d_rays + done, chunk, d_hits + done, cursor);
+        k_trace_bvh<false, NODES_WIDE><<<grid, T, 0, st>>>(s->dev, d_rays + done, chunk, d_hits + done, cursor);
       else
-        k_trace_bvh<false, false><<<grid, T, 0, st>>>(s->dev, d_rays + done, chunk, d_hits + done, cursor);
+        k_trace_bvh<false, NODES_PAIR><<<grid, T, 0, st>>>(s->dev, d_rays + done, chunk, d_hits + done, cursor);
       done += chunk;
     }
     RTW_CUDA_TRY(cudaFreeAsync(cursor, st));

@@ -105,10 +105,16 @@ __device__ __forceinline__ void stage_top_tree(const SceneDev& sc, float4* top_s
 // published with a "pending" mark, the next launch restarts the ray with that hit as its t_max (the result of a
 // closest-hit query does not depend on how it is split — same tie rule), and the shade kernel leaves pending
 // slots alone.  A restarted ray is never suspended again, so every ray finishes within two launches.
-// WIDE = walk the 4-wide view (SceneDev::nodes4): one 128-byte record and four slab tests per step, half the
-// dependent fetches of the pair walk — for hierarchies that do not fit the caches, where a step costs a DRAM
-// round trip (config C5).
-template <bool COUNT, bool MEDIA, bool WIDE = false, class IO>
+// NODES selects the node records the walk reads:
+//   NODES_PAIR    64-byte fp32 child pairs (SceneDev::nodes) — the default; bit-identical boxes to the build
+//   NODES_WIDE    128-byte records with the four grandchild boxes (SceneDev::nodes4): half the dependent fetches,
+//                 more bytes — measured slower everywhere, experiment only (RTW_WIDE=1)
+//   NODES_COMPACT 32-byte pairs with 16-bit boxes on the scene grid (SceneDev::nodes_c): half the bytes of a step for
+//                 36 decode instructions — for hierarchies that live in HBM, where traversal runs at the memory
+//                 system's random-gather bandwidth (config C5)
+enum { NODES_PAIR = 0, NODES_WIDE = 1, NODES_COMPACT = 2 };
+
+template <bool COUNT, bool MEDIA, int NODES = NODES_PAIR, class IO>
 __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, uint32_t count, uint32_t* cursor,
                                                     TraverseCounters& cnt, const float4* top_smem = nullptr) {
   const uint32_t lane = threadIdx.x & 31;
@@ -217,7 +223,7 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
           __any_sync(0xffffffffu, active && (pl_meta != 0u || (link < 0 && link != RTW_LINK_DONE))))
         break;
 #endif
-      if (WIDE && searching) {
+      if (NODES == NODES_WIDE && searching) {
         const float4* __restrict__ n = sc.nodes4 + 8 * (size_t)link;
         if (COUNT) cnt.pairs += 2;
         const float INF = __int_as_float(0x7f800000);
@@ -257,7 +263,45 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
           link = RTW_LINK_DONE;
         }
       }
-      if (!WIDE && searching) {
+      if (NODES == NODES_COMPACT && searching) {
+        const uint4* __restrict__ nc = sc.nodes_c + 2 * (size_t)link;
+        const uint4 a = __ldg(nc), b = __ldg(nc + 1);
+        if (COUNT) cnt.pairs++;
+        const float sx = sc.grid_step[0], sy = sc.grid_step[1], sz = sc.grid_step[2];
+        const float gx = sc.grid_lo[0], gy = sc.grid_lo[1], gz = sc.grid_lo[2];
+        // the same expression k_build_compact verified the containment with
+        const float4 l0 = make_float4(__fmaf_rn((float)(a.x & 0xffffu), sx, gx), __fmaf_rn((float)(a.x >> 16), sy, gy),
+                                      __fmaf_rn((float)(a.y & 0xffffu), sz, gz), 0.f);
+        const float4 l1 = make_float4(__fmaf_rn((float)(a.y >> 16), sx, gx), __fmaf_rn((float)(a.z & 0xffffu), sy, gy),
+                                      __fmaf_rn((float)(a.z >> 16), sz, gz), 0.f);
+        const float4 r0 = make_float4(__fmaf_rn((float)(b.x & 0xffffu), sx, gx), __fmaf_rn((float)(b.x >> 16), sy, gy),
+                                      __fmaf_rn((float)(b.y & 0xffffu), sz, gz), 0.f);
+        const float4 r1 = make_float4(__fmaf_rn((float)(b.y >> 16), sx, gx), __fmaf_rn((float)(b.z & 0xffffu), sy, gy),
+                                      __fmaf_rn((float)(b.z >> 16), sz, gz), 0.f);
+        // child word -> (link, meta): internal pair index, or leaf 0x80000000 | (count - 1) << 26 | first slot
+        const int32_t ll = (a.w & 0x80000000u) ? ~(int32_t)(a.w & 0x3FFFFFFu) : (int32_t)a.w;
+        const int32_t rl = (b.w & 0x80000000u) ? ~(int32_t)(b.w & 0x3FFFFFFu) : (int32_t)b.w;
+        const uint32_t lm = ((a.w >> 26) & 31u) + 1u, rm = ((b.w >> 26) & 31u) + 1u;
+        float tl, tr;
+        const bool hl = slab(l0, l1, o, inv, t_min, best_t, tl);
+        const bool hr = slab(r0, r1, o, inv, t_min, best_t, tr);
+        if (hl && hr) {
+          const bool left_first = tl <= tr;
+          stack[sp++] = left_first ? make_int2(rl, (int)rm) : make_int2(ll, (int)lm);
+          link = left_first ? ll : rl;
+          meta = left_first ? lm : rm;
+        } else if (hl) {
+          link = ll; meta = lm;
+        } else if (hr) {
+          link = rl; meta = rm;
+        } else if (sp > 0) {
+          const int2 e = stack[--sp];
+          link = e.x; meta = (uint32_t)e.y;
+        } else {
+          link = RTW_LINK_DONE;
+        }
+      }
+      if (NODES == NODES_PAIR && searching) {
 #if RTW_TOP_TREE > 0 && RTW_TOP_TREE_GENERIC
         // generic loads: the pair lies in shared memory (top of the tree) or in global memory
         const float4* n = (link & RTW_LINK_TOP) ? top_smem + 4 * (size_t)(link & (RTW_LINK_TOP - 1))
