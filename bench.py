@@ -305,9 +305,10 @@ def main():
         pairs_per_seg = sc.node_visits / max(sc.segments, 1)
         prims_per_seg = sc.prim_tests / max(sc.segments, 1)
         prim_bytes_per_seg = sc.prim_bytes / max(sc.segments, 1)
-        # per segment: 64 B per child-pair fetch + geometry bytes of the primitive tests
-        #            + ray read 32 B + hit write 8 B (identity slot mapping: no queue entry)
-        bytes_per_seg = 64.0 * pairs_per_seg + prim_bytes_per_seg + 32 + 8
+        # per segment: 64 B per child-pair fetch (32 B when rtw_build chose compact pairs) + geometry bytes of the
+        #            primitive tests + ray read 32 B + hit write 8 B (identity slot mapping: no queue entry)
+        node_bytes = float(sc.node_record_bytes) or 64.0
+        bytes_per_seg = node_bytes * pairs_per_seg + prim_bytes_per_seg + 32 + 8
         p_tim = scene.params(w, h, spp, seed=SEED, pool_size=args.pool, slices=args.slices, flags=rtw.RTW_RENDER_TIME_KERNELS)
         p_tim = rdist.partition(p_tim, rank, world) if world > 1 else p_tim
         stt = scene.render_device(cam, p_tim, accum.data_ptr(), stream.cuda_stream)
@@ -327,7 +328,7 @@ def main():
         roofline = {"bound": "hbm", "kernel": "k_wave_traverse", "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                     "bytes_per_launch": bytes_per_seg * seg_per_launch,
-                    "bytes_per_segment": bytes_per_seg, "pairs_per_segment": pairs_per_seg,
+                    "bytes_per_segment": bytes_per_seg, "pairs_per_segment": pairs_per_seg, "node_record_bytes": node_bytes,
                     "prim_tests_per_segment": prims_per_seg, "launches": stt.iterations,
                     "mean_launch_ms": stt.ms_traverse / max(stt.iterations, 1),
                     "traverse_share_of_step": stt.ms_traverse / max(stt.ms_traverse + stt.ms_shade, 1e-9),
@@ -336,7 +337,12 @@ def main():
                              "served from cache, so `frac` is a cache-bandwidth figure against the HBM peak and may exceed 1; "
                              "`hbm_only` counts the wavefront-state bytes that do cross HBM (ncu traffic agrees). The kernel is "
                              "issue-bound: see profiles/r01_final_ncu_summary.txt" % scene.build_stats.device_bytes)
-                    if resident else "scene exceeds L2: node / primitive fetches are HBM traffic"}
+                    if resident else "scene exceeds L2: node / primitive fetches are random gathers from HBM, which this GPU "
+                    "serves at ~1.3 TB/s (tools/gather_peak.cu, profiles/r01_gather_peak.txt) - 20 % of the copy peak used "
+                    "as `peak` here; see DESIGN.md section 6"}
+        if not resident:
+            roofline["gather_peak"] = {"value": 1290.0, "unit": "GB/s", "source": "profiles/r01_gather_peak.txt (64 B independent "
+                                       "gathers over 1.4 GB, measured on this pool's B200)"}
 
     base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

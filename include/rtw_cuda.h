@@ -101,7 +101,7 @@ typedef struct rtw_render_params {
 typedef struct rtw_render_stats {
   uint64_t segments;      /* path segments = world.hit() queries (lib.rs:102)              */
   uint64_t paths;         /* camera paths started                                          */
-  uint64_t node_visits;   /* 64-byte child-pair fetches (only with COUNT_TRAVERSAL)        */
+  uint64_t node_visits;   /* child-pair fetches (only with COUNT_TRAVERSAL)                */
   uint64_t prim_tests;    /* primitive intersection tests (only with COUNT_TRAVERSAL)      */
   uint64_t prim_bytes;    /* bytes those tests fetched: 4 (slot meta) + geometry: sphere   */
                           /*   16, rect 32, moving sphere / triangle 48 (COUNT_TRAVERSAL)  */
@@ -112,7 +112,8 @@ typedef struct rtw_render_stats {
   float ms_render;        /* CUDA-event time of the render, first launch to last           */
   float ms_traverse;      /* summed CUDA-event time of the traversal kernel (if timed)     */
   float ms_shade;         /* summed CUDA-event time of the shade kernel (if timed)         */
-  float reserved;
+  float node_record_bytes;/* bytes one node_visit fetches: 64 (fp32 pair) or 32 (compact    */
+                          /*   pair, hierarchies beyond the caches); 0 = not applicable      */
 } rtw_render_stats;
 
 typedef struct rtw_build_stats {

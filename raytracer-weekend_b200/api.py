@@ -58,10 +58,10 @@ class RenderStats(C.Structure):
     _fields_ = [("segments", C.c_uint64), ("paths", C.c_uint64), ("node_visits", C.c_uint64), ("prim_tests", C.c_uint64),
                 ("prim_bytes", C.c_uint64),
                 ("iterations", C.c_uint32), ("launches", C.c_uint32), ("pool_size", C.c_uint32), ("slices", C.c_uint32),
-                ("ms_render", C.c_float), ("ms_traverse", C.c_float), ("ms_shade", C.c_float), ("reserved", C.c_float)]
+                ("ms_render", C.c_float), ("ms_traverse", C.c_float), ("ms_shade", C.c_float), ("node_record_bytes", C.c_float)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 # rtw_frame_callback (include/rtw_cuda.h)

@@ -870,6 +870,7 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
     stats->ms_render = ms;
     stats->ms_traverse = ms_t;
     stats->ms_shade = ms_s;
+    stats->node_record_bytes = compact ? 32.f : (wide ? 128.f : 64.f);
   }
   return RTW_OK;
 }

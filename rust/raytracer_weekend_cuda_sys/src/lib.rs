@@ -98,7 +98,7 @@ pub struct rtw_render_stats {
     pub ms_render: f32,
     pub ms_traverse: f32,
     pub ms_shade: f32,
-    pub reserved: f32,
+    pub node_record_bytes: f32,
 }
 
 #[repr(C)]
