@@ -332,7 +332,9 @@ def test_alternative_node_records_keep_parity(gpu, oracle, monkeypatch, env, rec
                     assert_hits_equal(hg, ho, f"{env} {scene} bounce {bounce}")
             p = sg.params(64, 36, 3, seed=5, slices=1, flags=rtw.RTW_RENDER_COUNT_TRAVERSAL)
             ag, stg = sg.render(cam, p)
-            if env == "RTW_COMPACT":   # (the counting variant of the 4-wide walk does not exist: it counts the pair walk)
+            if env == "RTW_COMPACT" and scene != "cornell-box":
+                # (the flat Cornell scene has an empty right child, which the compact encoding refuses: it keeps its
+                # fp32 pair; the counting variant of the 4-wide walk does not exist: it counts the pair walk)
                 assert stg.node_record_bytes == record_bytes
             if scene == "cornell-box":
                 ao, sto = so.render(cam, so.params(64, 36, 3, seed=5, slices=1))
