@@ -205,6 +205,8 @@ def host_lib():
         h.rtwh_perlin_new.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         h.rtwh_load_obj.argtypes = [C.c_char_p, C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        h.rtwh_parse_obj.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
+        h.rtwh_parse_obj.restype = C.c_longlong
         h.rtwh_progress_image_start.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t]
         h.rtwh_progress_pixel.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_float), C.c_void_p, C.c_size_t]
         h.rtwh_progress_image_end.argtypes = [C.c_void_p, C.c_size_t]
@@ -215,6 +217,16 @@ def host_lib():
         h.rtwh_set_asset_dir(ASSET_DIR.encode())
         _host_lib = h
     return _host_lib
+
+
+def parse_obj(path: str, mode: int = 0, threads: int = 0):
+    """OBJ ingest (triangular.rs:170-260 semantics): mode 0 = the parallel parser of the product path, 1 = the
+    single-threaded reference parser.  Returns (triangles, checksum over every output array, seconds)."""
+    cs, sec = C.c_uint64(), C.c_double()
+    n = host_lib().rtwh_parse_obj(path.encode(), mode, threads, C.byref(cs), C.byref(sec))
+    if n < 0:
+        raise RtwError(host_lib().rtwh_capi_error().decode())
+    return int(n), int(cs.value), float(sec.value)
 
 
 def progress_frame(accum: np.ndarray, spp: int) -> bytes:

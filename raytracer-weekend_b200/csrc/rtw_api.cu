@@ -7,6 +7,7 @@
 #include <future>
 #include <cstring>
 #include <string>
+#include <thread>
 
 #include "rtw_scene.cuh"
 
@@ -356,39 +357,53 @@ int rtw_add_triangles(rtw_scene* s, uint32_t n, const float* vertices, const flo
     return set_error(RTW_ERR_INVALID, "triangles: bad material id");
   }
   if (s->prim_meta.size() + (size_t)n >= (size_t)0x0FFFFFFF) return set_error(RTW_ERR_UNSUPPORTED, "too many primitives");
-  int first = (int)s->prim_meta.size();
+  if (s->medium_material >= 0) return set_error(RTW_ERR_UNSUPPORTED, "medium: the boundary must be one sphere or one cuboid");
+  const int first = (int)s->prim_meta.size();
   const bool shaded = normals || uvs;
-  s->raw_geom.reserve(s->raw_geom.size() + 3 * (size_t)n);
-  s->prim_meta.reserve(s->prim_meta.size() + n);
-  s->prim_mat.reserve(s->prim_mat.size() + n);
-  s->prim_shade.reserve(s->prim_shade.size() + n);
-  if (shaded) s->tri_shade.reserve(s->tri_shade.size() + n);
-  for (uint32_t i = 0; i < n; ++i) {
-    const float* v = vertices + 9 * (size_t)i;
-    int shade = -1;
-    if (shaded) {
-      TriShade ts;
-      if (normals) {
-        memcpy(ts.n, normals + 9 * (size_t)i, 9 * sizeof(float));
-      } else {  // triangular.rs:47-55: un-normalised face normal for all three vertices
-        v3 a = mk(v[0], v[1], v[2]), b = mk(v[3], v[4], v[5]), c = mk(v[6], v[7], v[8]);
-        v3 fn = cross(b - a, c - a);
-        for (int k = 0; k < 3; ++k) { ts.n[3 * k] = fn.x; ts.n[3 * k + 1] = fn.y; ts.n[3 * k + 2] = fn.z; }
+  const uint32_t meta = PT_TRI | ((uint32_t)current_instance(s) << RTW_META_TYPE_BITS);
+  const size_t shade0 = s->tri_shade.size();
+  // bulk ingest: the arrays grow once and are filled by all host threads (a 10 M-triangle mesh is 0.5 GB of copies)
+  s->raw_geom.resize(s->raw_geom.size() + 3 * (size_t)n);
+  s->prim_meta.resize(s->prim_meta.size() + n, meta);
+  s->prim_mat.resize(s->prim_mat.size() + n, (uint32_t)material);
+  s->prim_shade.resize(s->prim_shade.size() + n, -1);
+  if (shaded) s->tri_shade.resize(shade0 + n);
+  auto fill = [&](uint32_t lo, uint32_t hi) {
+    for (uint32_t i = lo; i < hi; ++i) {
+      const float* v = vertices + 9 * (size_t)i;
+      const size_t id = (size_t)first + i;
+      if (shaded) {
+        TriShade& ts = s->tri_shade[shade0 + i];
+        if (normals) {
+          memcpy(ts.n, normals + 9 * (size_t)i, 9 * sizeof(float));
+        } else {  // triangular.rs:47-55: un-normalised face normal for all three vertices
+          v3 a = mk(v[0], v[1], v[2]), b = mk(v[3], v[4], v[5]), c = mk(v[6], v[7], v[8]);
+          v3 fn = cross(b - a, c - a);
+          for (int k = 0; k < 3; ++k) { ts.n[3 * k] = fn.x; ts.n[3 * k + 1] = fn.y; ts.n[3 * k + 2] = fn.z; }
+        }
+        if (uvs) {
+          memcpy(ts.uv, uvs + 6 * (size_t)i, 6 * sizeof(float));
+        } else {  // triangular.rs:57-65
+          const float def[6] = {0.f, 0.f, 1.f, 0.f, 0.f, 1.f};
+          memcpy(ts.uv, def, sizeof(def));
+        }
+        ts.pad = 0.f;
+        s->prim_shade[id] = (int32_t)(shade0 + i);
       }
-      if (uvs) {
-        memcpy(ts.uv, uvs + 6 * (size_t)i, 6 * sizeof(float));
-      } else {  // triangular.rs:57-65
-        const float def[6] = {0.f, 0.f, 1.f, 0.f, 0.f, 1.f};
-        memcpy(ts.uv, def, sizeof(def));
-      }
-      ts.pad = 0.f;
-      shade = (int)s->tri_shade.size();
-      s->tri_shade.push_back(ts);
+      if (material_ids) s->prim_mat[id] = (uint32_t)material_ids[i];
+      s->raw_geom[3 * id] = make_float4(v[0], v[1], v[2], v[3]);
+      s->raw_geom[3 * id + 1] = make_float4(v[4], v[5], v[6], v[7]);
+      s->raw_geom[3 * id + 2] = make_float4(v[8], 0, 0, 0);
     }
-    int m = material_ids ? material_ids[i] : material;
-    int id = emit_prim(s, PT_TRI, make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]),
-                       make_float4(v[8], 0, 0, 0), m, shade);
-    if (id < 0) return id;
+  };
+  const uint32_t workers = n >= (1u << 16) ? std::max(1u, std::min(std::thread::hardware_concurrency(), 32u)) : 1u;
+  if (workers <= 1) {
+    fill(0, n);
+  } else {
+    std::vector<std::thread> th;
+    for (uint32_t w = 0; w < workers; ++w)
+      th.emplace_back(fill, (uint32_t)((uint64_t)n * w / workers), (uint32_t)((uint64_t)n * (w + 1) / workers));
+    for (auto& t : th) t.join();
   }
   return first;
 }

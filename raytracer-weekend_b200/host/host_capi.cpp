@@ -1,8 +1,10 @@
 // C entry points of the host front end (librtw_host.so) for harnesses that are not C++
 // (the pytest suite and bench.py drive it through ctypes).  Exceptions become error codes +
 // rtwh_last_error().
+#include <chrono>
 #include <cstring>
 
+#include "obj_loader.hpp"
 #include "rtw_host.hpp"
 
 namespace rtwh {
@@ -133,6 +135,40 @@ int rtwh_load_obj(const char* path, uint32_t* ntris, float* verts, float* normal
     if (normals && !cap.n.empty()) memcpy(normals, cap.n.data(), cap.n.size() * 4);
     if (uvs && !cap.uv.empty()) memcpy(uvs, cap.uv.data(), cap.uv.size() * 4);
     return RTW_OK;
+  } catch (const std::exception& e) {
+    return fail(RTW_ERR_INVALID, e.what());
+  }
+}
+
+// OBJ ingest check / benchmark: parse `path` with the parallel parser (mode 0, `threads` <= 0: all) or with the
+// single-threaded reference parser (mode 1).  Returns the triangle count; checksum = FNV-1a over every output array
+// (positions, normals, uvs, presence flags, per-face material names), so two parses can be compared without moving
+// the arrays across the boundary; seconds = wall time of the parse.
+long long rtwh_parse_obj(const char* path, int mode, int threads, uint64_t* checksum, double* seconds) {
+  if (!path) return fail(RTW_ERR_INVALID, "parse_obj: path is NULL");
+  try {
+    auto t0 = std::chrono::steady_clock::now();
+    rtwh::ObjData d = mode == 0 ? rtwh::parse_obj_fast(path, threads) : rtwh::parse_obj_simple(path);
+    if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (checksum) {
+      uint64_t h = 1469598103934665603ull;
+      auto mix = [&](const void* p, size_t n) {
+        const uint8_t* b = (const uint8_t*)p;
+        for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+      };
+      mix(d.v.data(), d.v.size() * 4); mix(d.n.data(), d.n.size() * 4); mix(d.uv.data(), d.uv.size() * 4);
+      mix(d.has_n.data(), d.has_n.size()); mix(d.has_uv.data(), d.has_uv.size());
+      for (int32_t mi : d.face_mtl) {
+        const std::string name = mi < 0 ? std::string() : d.mtl_names[(size_t)mi];
+        mix(name.data(), name.size());
+        mix("|", 1);
+      }
+      mix(d.mtllib.data(), d.mtllib.size());
+      const uint8_t flags[2] = {(uint8_t)d.all_normals, (uint8_t)d.all_uvs};
+      mix(flags, 2);
+      *checksum = h;
+    }
+    return (long long)d.triangles();
   } catch (const std::exception& e) {
     return fail(RTW_ERR_INVALID, e.what());
   }

@@ -1,6 +1,7 @@
 // Host front end implementation: sink loading, flatten(), Camera::new, Perlin::new, the OBJ/MTL
 // loader and the Raytracer facade.  See rtw_host.hpp.  Compiled with -ffp-contract=off.
 #include "rtw_host.hpp"
+#include "obj_loader.hpp"
 
 #include <dlfcn.h>
 
@@ -557,26 +558,21 @@ std::shared_ptr<ImageTexture> ImageTexture::open(const std::string& path) {
 // ---------------------------------------------------------------------------------------------
 namespace {
 
-struct ObjData {
-  std::vector<float> v, n, uv;               // per triangle, file order
-  std::vector<std::string> face_material;    // "" = no usemtl in effect
-  bool all_normals = true, all_uvs = true;
-  std::string mtllib;
-  std::vector<uint8_t> has_n, has_uv;         // per triangle
-};
-
 int resolve_index(long idx, size_t count, const std::string& path) {
   long r = idx > 0 ? idx - 1 : (long)count + idx;
   if (idx == 0 || r < 0 || r >= (long)count) throw Error("OBJ index out of range in " + path);
   return (int)r;
 }
 
-ObjData parse_obj(const std::string& path) {
+}  // namespace
+
+ObjData parse_obj_simple(const std::string& path) {
   std::ifstream f(path);
   if (!f) throw Error("cannot open OBJ file: " + path);
   std::vector<double> pos, tex, nrm;
   ObjData out;
   std::string line, cur_mtl;
+  std::map<std::string, int32_t> mtl_index;
   while (std::getline(f, line)) {
     std::istringstream ss(line);
     std::string tag;
@@ -628,12 +624,23 @@ ObjData parse_obj(const std::string& path) {
         out.has_n.push_back(hn); out.has_uv.push_back(ht);
         out.all_normals = out.all_normals && hn;
         out.all_uvs = out.all_uvs && ht;
-        out.face_material.push_back(cur_mtl);
+        int32_t mi = -1;
+        if (!cur_mtl.empty()) {
+          auto it = mtl_index.find(cur_mtl);
+          if (it == mtl_index.end()) {
+            it = mtl_index.emplace(cur_mtl, (int32_t)out.mtl_names.size()).first;
+            out.mtl_names.push_back(cur_mtl);
+          }
+          mi = it->second;
+        }
+        out.face_mtl.push_back(mi);
       }
     }
   }
   return out;
 }
+
+namespace {
 
 // triangular.rs:278-312
 std::map<std::string, MaterialPtr> parse_mtl(const std::string& path) {
@@ -685,12 +692,13 @@ std::shared_ptr<TriangleMesh> load_mesh(const std::string& path, MaterialPtr mat
   auto it = mesh_registry().find(path);
   if (it != mesh_registry().end()) return std::make_shared<TriangleMesh>(it->second.v, it->second.n, it->second.uv, material);
   if (file_exists(path) && path.size() > 4 && path.substr(path.size() - 4) == ".obj") {
-    ObjData d = parse_obj(path);
+    ObjData d = parse_obj_fast(path);
     bool any_n = false, any_uv = false;
     for (auto h : d.has_n) any_n = any_n || h;
     for (auto h : d.has_uv) any_uv = any_uv || h;
     fill_defaults(d);
-    return std::make_shared<TriangleMesh>(d.v, any_n ? d.n : std::vector<float>(), any_uv ? d.uv : std::vector<float>(), material);
+    return std::make_shared<TriangleMesh>(std::move(d.v), any_n ? std::move(d.n) : std::vector<float>(),
+                                          any_uv ? std::move(d.uv) : std::vector<float>(), material);
   }
   MeshAsset a;
   if (read_rtwm(asset_dir() + "/" + stem_of(path) + ".rtwm", a) || read_rtwm(path, a))
@@ -703,19 +711,21 @@ HittablePtr load_wavefront_obj(const std::string& path, MaterialPtr override_mat
   if (override_material) {
     tris.push_back(load_mesh(path, override_material));
   } else if (file_exists(path)) {
-    ObjData d = parse_obj(path);
+    ObjData d = parse_obj_fast(path);
     std::map<std::string, MaterialPtr> lib;
     bool have_lib = false;
     if (!d.mtllib.empty()) { lib = parse_mtl(dir_of(path) + "/" + d.mtllib); have_lib = true; }
     MaterialPtr magenta = std::make_shared<DiffuseLight>(SolidColor::new_rgb(1.0f, 0.0f, 1.0f));  // triangular.rs:181
-    std::vector<MaterialPtr> per_face;
-    for (const auto& name : d.face_material) {
-      if (name.empty()) { per_face.push_back(magenta); continue; }
+    std::vector<MaterialPtr> by_index;
+    for (const auto& name : d.mtl_names) {
       if (!have_lib) throw Error("OBJ uses usemtl without mtllib (triangular.rs:177-179 unwraps None): " + path);
       auto m = lib.find(name);
       if (m == lib.end()) throw Error("OBJ material not found in MTL: " + name);
-      per_face.push_back(m->second);
+      by_index.push_back(m->second);
     }
+    std::vector<MaterialPtr> per_face;
+    per_face.reserve(d.face_mtl.size());
+    for (int32_t mi : d.face_mtl) per_face.push_back(mi < 0 ? magenta : by_index[(size_t)mi]);
     bool any_n = false, any_uv = false;
     for (auto h : d.has_n) any_n = any_n || h;
     for (auto h : d.has_uv) any_uv = any_uv || h;

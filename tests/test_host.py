@@ -200,3 +200,92 @@ def test_oracle_render_frames_equals_frame_by_frame(oracle):
         for i, c in enumerate([cam, cam2]):
             a, st = s.render(c, s.params(24, 24, 3, seed=11 + i))
             assert np.array_equal(a, got[i][0]) and st.segments == got[i][1]
+
+
+# ---- OBJ ingest fast path: the parallel parser must reproduce the reference parser exactly -------
+TRICKY_OBJ = """# comment line, CRLF endings, signs, exponents, negative indices, quads, mixed corner forms\r
+mtllib lib.mtl\r
+v 0 0 0\r
+v 1.5 +2.25 -3e-1
+v 1 1 0   # trailing comment tokens are ignored by `>>`-style parsing of three numbers
+v 0 1 0
+v 0.1 0.2
+vt 0 0
+vt 1 0
+vt 1 1
+vn 0 0 1
+vn 0 1 0
+g group1
+usemtl first
+f 1/1/1 2/2/1 3/3/1 4/1/1
+f -5 -4 -3
+usemtl second
+f 1//2 2//2 3//2
+s off
+f 1/1 2/2 3/3 4/3 5/1
+usemtl
+f 3 2 1
+v 9 9 9
+f -1 1 2
+"""
+
+
+def test_parallel_obj_parser_equals_the_reference_parser(tmp_path):
+    obj = tmp_path / "tricky.obj"
+    obj.write_bytes(TRICKY_OBJ.encode())
+    ref = rtw.parse_obj(str(obj), mode=1)
+    assert ref[0] == 2 + 1 + 1 + 3 + 1 + 1                      # quads / pentagon fan-triangulated
+    for threads in (1, 2, 3, 8):
+        got = rtw.parse_obj(str(obj), mode=0, threads=threads)
+        assert got[:2] == ref[:2], threads
+    # a file large enough to be cut into many chunks (>= 64 KiB each): vertices first, faces after, materials changing
+    rs = np.random.RandomState(3)
+    nv, nf = 20000, 60000
+    lines = ["mtllib x.mtl\n"]
+    lines += ["v %.6f %.6f %.6f\n" % tuple(r) for r in rs.uniform(-50, 50, (nv, 3))]
+    lines += ["vn %.4f %.4f %.4f\n" % tuple(r) for r in rs.uniform(-1, 1, (nv, 3))]
+    lines += ["vt %.5f %.5f\n" % tuple(r) for r in rs.uniform(0, 1, (nv, 2))]
+    for i, (a, b, c, d) in enumerate(rs.randint(1, nv + 1, (nf, 4))):
+        if i % 7000 == 0:
+            lines.append("usemtl m%d\n" % (i // 7000 % 3))
+        kind = i % 4
+        if kind == 0:
+            lines.append("f %d/%d/%d %d/%d/%d %d/%d/%d\n" % (a, a, a, b, b, b, c, c, c))
+        elif kind == 1:
+            lines.append("f %d//%d %d//%d %d//%d %d//%d\n" % (a, a, b, b, c, c, d, d))
+        elif kind == 2:
+            lines.append("f %d %d %d\n" % (a - nv - 1, b - nv - 1, c - nv - 1))      # relative indices
+        else:
+            lines.append("f %d/%d %d/%d %d/%d\n" % (a, a, b, b, c, c))
+    big = tmp_path / "big.obj"
+    big.write_text("".join(lines))
+    ref = rtw.parse_obj(str(big), mode=1)
+    assert ref[0] == nf + nf // 4
+    for threads in (1, 4, 0):
+        assert rtw.parse_obj(str(big), mode=0, threads=threads)[:2] == ref[:2], threads
+
+
+def test_parallel_obj_parser_reports_the_same_errors(tmp_path):
+    bad = tmp_path / "bad.obj"
+    bad.write_text("v 0 0 0\nv 1 0 0\nf 1 2\n")
+    for mode in (0, 1):
+        with pytest.raises(rtw.RtwError, match="points / lines"):
+            rtw.parse_obj(str(bad), mode=mode)
+    bad.write_text("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 4\n")
+    for mode in (0, 1):
+        with pytest.raises(rtw.RtwError, match="index out of range"):
+            rtw.parse_obj(str(bad), mode=mode)
+    bad.write_text("v 0 0 0\nv 1 0 0\nf 1 2 3\nv 0 1 0\n")         # forward reference: vertex 3 is defined after the face
+    for mode in (0, 1):
+        with pytest.raises(rtw.RtwError, match="index out of range"):
+            rtw.parse_obj(str(bad), mode=mode)
+    with pytest.raises(rtw.RtwError, match="cannot open"):
+        rtw.parse_obj(str(tmp_path / "missing.obj"))
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_MODELS), reason="reference models are only present in the build container")
+@pytest.mark.parametrize("stem", ["cow-nonormals", "monument_downscaled_polygon_reduced", "capsule", "Normals_Try3"])
+def test_parallel_obj_parser_on_the_reference_models(stem):
+    ref = rtw.parse_obj(f"{REF_MODELS}/{stem}.obj", mode=1)
+    for threads in (1, 0):
+        assert rtw.parse_obj(f"{REF_MODELS}/{stem}.obj", mode=0, threads=threads)[:2] == ref[:2]
