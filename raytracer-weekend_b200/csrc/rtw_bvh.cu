@@ -419,6 +419,7 @@ __global__ void k_build_wide(uint32_t num_nodes, const float4* __restrict__ node
   for (int k = 0; k < 8; ++k) nodes4[8 * (size_t)i + k] = out[k];
 }
 
+#if RTW_TOP_TREE > 0
 // Kernel (one thread): the first `cap` pairs of the tree in breadth-first order, for the shared-memory top of
 // tree of the traversal kernels.  A child link that points to a pair inside the copy is re-targeted to its index
 // in the copy and tagged RTW_LINK_TOP; every other link (deeper pairs, leaves) is kept.
@@ -442,6 +443,7 @@ __global__ void k_top_tree(const float4* __restrict__ nodes, uint32_t num_nodes,
   }
   *top_count = n;
 }
+#endif
 
 // Kernel: leaves.  Slot s holds primitive vals[s]; copies its geometry and meta into slot order.
 __global__ void k_emit_leaves(uint32_t n, const uint32_t* __restrict__ vals, const float4* __restrict__ enc,

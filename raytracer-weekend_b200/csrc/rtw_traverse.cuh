@@ -133,7 +133,9 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
   float time = 0.f, t_min = 0.f, best_t = 0.f;
   int32_t best_slot = -1, best_id = -2, link = RTW_LINK_DONE, pl_link = 0;
   uint32_t best_meta = 0, meta = 0, pl_meta = 0, cur_inst = 0, cur_pm = 0xffffffffu;
+#if RTW_RECT_PERM_CACHE
   float oA = 0.f, oB = 0.f, oK = 0.f, dA = 0.f, dB = 0.f, dK = 0.f;  // ray permuted for the current rectangle run
+#endif
   int2 stack[RTW_STACK_SIZE];
   int sp = 0;
 #if RTW_CURSOR_CHUNKS
