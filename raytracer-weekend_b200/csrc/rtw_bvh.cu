@@ -728,7 +728,7 @@ int build_scene_device(rtw_scene* s, float time0, float time1, rtw_build_stats* 
   rp.max_leaf = 32;
   uint32_t flat_max = 32;
   if (const char* e = getenv("RTW_SAH_PAIR_COST")) rp.c_pair = (float)atof(e);
-  if (const char* e = getenv("RTW_MAX_LEAF")) rp.max_leaf = (uint32_t)std::max(1, atoi(e));
+  if (const char* e = getenv("RTW_MAX_LEAF")) rp.max_leaf = (uint32_t)std::min(std::max(1, atoi(e)), 32);  // 5 bits in a packed child reference
   if (const char* e = getenv("RTW_FLAT_SCENE_MAX")) flat_max = (uint32_t)std::max(0, atoi(e));
   rp.force_flat = (n <= flat_max && n <= rp.max_leaf) ? 1u : 0u;
   k_refit<<<G, T>>>(n, d_v0, d_lo, d_hi, rp, d_nparent, d_lparent, d_nrange, d_flags, d_heights, d_ncost, d_collapsed,

@@ -48,6 +48,26 @@ namespace rtw {
 #define RTW_TOP_TREE_GENERIC 0  // RTW_TOP_TREE > 0 only: generic loads instead of an LDS / LDG branch
 #endif
 // RTW_TOP_TREE (rtw_device.cuh): shared-memory copy of the top of the tree — 5-14 % slower, default 0.
+#ifndef RTW_STACK_PACKED
+#define RTW_STACK_PACKED 0      // 4-byte stack entries (leaf: 0x80000000 | (count - 1) << 26 | first slot) instead of int2: 2-4 % slower
+#endif
+
+// The traversal stack lives in local memory (96 entries per lane); an entry is a child reference (link, meta).
+#if RTW_STACK_PACKED
+typedef uint32_t StackEntry;  // needs first slot < 2^26 and leaves of <= 32 primitives
+__device__ __forceinline__ StackEntry stack_pack(int32_t link, uint32_t meta) {
+  return link >= 0 ? (uint32_t)link : (0x80000000u | ((meta - 1u) << 26) | (uint32_t)(~link));
+}
+__device__ __forceinline__ void stack_unpack(StackEntry e, int32_t& link, uint32_t& meta) {
+  const bool leaf = (e & 0x80000000u) != 0u;
+  link = leaf ? ~(int32_t)(e & 0x3FFFFFFu) : (int32_t)e;
+  meta = leaf ? ((e >> 26) & 31u) + 1u : 0u;
+}
+#else
+typedef int2 StackEntry;
+__device__ __forceinline__ StackEntry stack_pack(int32_t link, uint32_t meta) { return make_int2(link, (int)meta); }
+__device__ __forceinline__ void stack_unpack(StackEntry e, int32_t& link, uint32_t& meta) { link = e.x; meta = (uint32_t)e.y; }
+#endif
 
 // Slab test of one child record against the ray: aabb.rs:23-48 with (a) the reciprocal hoisted out
 // of the node loop (1/d is the same value every time), (b) a NON-strict reject (the reference
@@ -136,7 +156,7 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
 #if RTW_RECT_PERM_CACHE
   float oA = 0.f, oB = 0.f, oK = 0.f, dA = 0.f, dB = 0.f, dK = 0.f;  // ray permuted for the current rectangle run
 #endif
-  int2 stack[RTW_STACK_SIZE];
+  StackEntry stack[RTW_STACK_SIZE];
   int sp = 0;
 #if RTW_CURSOR_CHUNKS
   uint32_t chunk_pos = 0, chunk_end = 0;  // warp-uniform: unused entries of the warp's current chunk
@@ -253,14 +273,13 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
         RTW_CSWAP(0, 1) RTW_CSWAP(2, 3) RTW_CSWAP(0, 2) RTW_CSWAP(1, 3) RTW_CSWAP(1, 2)
 #undef RTW_CSWAP
         // hits form a prefix; the farthest is pushed first so that the nearest of the rest is popped first
-        if (lk[3] != RTW_LINK_DONE) stack[sp++] = make_int2(lk[3], (int)mk4[3]);
-        if (lk[2] != RTW_LINK_DONE) stack[sp++] = make_int2(lk[2], (int)mk4[2]);
-        if (lk[1] != RTW_LINK_DONE) stack[sp++] = make_int2(lk[1], (int)mk4[1]);
+        if (lk[3] != RTW_LINK_DONE) stack[sp++] = stack_pack(lk[3], mk4[3]);
+        if (lk[2] != RTW_LINK_DONE) stack[sp++] = stack_pack(lk[2], mk4[2]);
+        if (lk[1] != RTW_LINK_DONE) stack[sp++] = stack_pack(lk[1], mk4[1]);
         if (lk[0] != RTW_LINK_DONE) {
           link = lk[0]; meta = mk4[0];
         } else if (sp > 0) {
-          const int2 e = stack[--sp];
-          link = e.x; meta = (uint32_t)e.y;
+          stack_unpack(stack[--sp], link, meta);
         } else {
           link = RTW_LINK_DONE;
         }
@@ -289,7 +308,7 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
         const bool hr = slab(r0, r1, o, inv, t_min, best_t, tr);
         if (hl && hr) {
           const bool left_first = tl <= tr;
-          stack[sp++] = left_first ? make_int2(rl, (int)rm) : make_int2(ll, (int)lm);
+          stack[sp++] = left_first ? stack_pack(rl, rm) : stack_pack(ll, lm);
           link = left_first ? ll : rl;
           meta = left_first ? lm : rm;
         } else if (hl) {
@@ -297,8 +316,7 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
         } else if (hr) {
           link = rl; meta = rm;
         } else if (sp > 0) {
-          const int2 e = stack[--sp];
-          link = e.x; meta = (uint32_t)e.y;
+          stack_unpack(stack[--sp], link, meta);
         } else {
           link = RTW_LINK_DONE;
         }
@@ -330,7 +348,7 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
           const bool left_first = tl <= tr;
           const int2 far = left_first ? make_int2(__float_as_int(r0.w), __float_as_int(r1.w))
                                       : make_int2(__float_as_int(l0.w), __float_as_int(l1.w));
-          stack[sp++] = far;
+          stack[sp++] = stack_pack(far.x, (uint32_t)far.y);
 #if RTW_PREFETCH_FAR
           // the postponed child is the likeliest later visit: start its 64-byte pair (or its first primitive)
           // on the way to L2 now — only matters when the hierarchy does not fit the caches (config C5)
@@ -344,8 +362,7 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
         } else if (hr) {
           link = __float_as_int(r0.w); meta = __float_as_uint(r1.w);
         } else if (sp > 0) {
-          const int2 e = stack[--sp];
-          link = e.x; meta = (uint32_t)e.y;
+          stack_unpack(stack[--sp], link, meta);
         } else {
           link = RTW_LINK_DONE;
         }
@@ -353,8 +370,7 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
         if (link < 0 && link != RTW_LINK_DONE && pl_meta == 0u) {  // first leaf in hand: postpone it, keep walking
           pl_link = link; pl_meta = meta;
           if (sp > 0) {
-            const int2 e = stack[--sp];
-            link = e.x; meta = (uint32_t)e.y;
+            stack_unpack(stack[--sp], link, meta);
           } else {
             link = RTW_LINK_DONE;
           }
@@ -376,8 +392,7 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
       } else {
         first = (uint32_t)(~link); nprim = meta;
         if (sp > 0) {
-          const int2 e = stack[--sp];
-          link = e.x; meta = (uint32_t)e.y;
+          stack_unpack(stack[--sp], link, meta);
         } else {
           link = RTW_LINK_DONE;
         }
