@@ -762,6 +762,11 @@ int build_scene_device(rtw_scene* s, float time0, float time1, rtw_build_stats* 
   RTW_CUDA_TRY(cudaMemcpy(h_root, d_root, sizeof(h_root), cudaMemcpyDeviceToHost));
   memcpy(s->root_box, h_root, 6 * sizeof(float));
   memcpy(&s->bvh_height, &h_root[6], 4);
+  {
+    uint32_t root_collapsed = 0;
+    memcpy(&root_collapsed, &h_root[7], 4);
+    d.flat_count = (root_collapsed && n <= 32) ? n : 0u;
+  }
   for (void* p : scratch) cudaFree(p);
 
   // compact pairs: only worth their decode instructions when the hierarchy lives in HBM (>= 2^20 primitives)

@@ -80,7 +80,7 @@ struct FrameDev {
 };
 
 // the traversal kernel variants a render can launch
-enum TravKind { TK_PAIR = 0, TK_MEDIA, TK_WIDE, TK_COMPACT, TK_COUNT, TK_COUNT_COMPACT, TK_N };
+enum TravKind { TK_PAIR = 0, TK_MEDIA, TK_WIDE, TK_COMPACT, TK_COUNT, TK_COUNT_COMPACT, TK_FLAT, TK_N };
 
 struct WaveHost {
   WaveDev dev{};
@@ -90,7 +90,7 @@ struct WaveHost {
   WaveCtl* pinned_ctl = nullptr;   // [RTW_MAX_SUBPOOLS][2]: ring for the lagging termination check
   cudaStream_t stream = nullptr;    // internal non-blocking stream (graph capture needs a non-legacy stream)
   cudaStream_t pool_stream[RTW_MAX_SUBPOOLS] = {};
-  int blocks_trav[6] = {0, 0, 0, 0, 0, 0};  // persistent grid per TravKind
+  int blocks_trav[TK_N] = {};  // persistent grid per TravKind
   int blocks_shade = 0;
 };
 
@@ -267,12 +267,12 @@ struct WaveIO {
 #ifndef RTW_TRAVERSE_MINBLOCKS
 #define RTW_TRAVERSE_MINBLOCKS 8
 #endif
-template <bool COUNT, bool MEDIA, int NODES>
-__global__ void __launch_bounds__(128, (COUNT || MEDIA || NODES == NODES_WIDE) ? 1 : RTW_TRAVERSE_MINBLOCKS)
-    k_wave_traverse(SceneDev sc, WaveDev w, uint32_t parity, uint32_t seed_lo, uint32_t seed_hi) {
+// Prologue of every traversal kernel of the wavefront: this iteration's entry count and input mode, and (one thread)
+// the bookkeeping for the shade kernel that follows.
+__device__ __forceinline__ void traverse_prologue(const WaveDev& w, uint32_t parity, uint32_t& count, uint32_t& in_queue) {
   WaveCtl* ctl = w.ctl;
-  const uint32_t count = ctl->count[parity];
-  const uint32_t in_queue = ctl->qmode[parity];
+  count = ctl->count[parity];
+  in_queue = ctl->qmode[parity];
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     ctl->cursor_shade = 0;  // consumed by the shade kernel that follows
     // What the shade kernel that follows writes for the next iteration: a queue once the work items have run
@@ -281,6 +281,25 @@ __global__ void __launch_bounds__(128, (COUNT || MEDIA || NODES == NODES_WIDE) ?
     ctl->qmode[parity ^ 1] = out_queue;
     ctl->count[parity ^ 1] = out_queue ? 0u : w.slot_count;
   }
+}
+
+// Flat scenes (<= 32 primitives in one leaf): rtw_traverse.cuh, traverse_flat
+__global__ void __launch_bounds__(128, 8) k_wave_traverse_flat(SceneDev sc, WaveDev w, uint32_t parity, uint32_t seed_lo,
+                                                               uint32_t seed_hi) {
+  __shared__ FlatRecords fr;
+  uint32_t count, in_queue;
+  traverse_prologue(w, parity, count, in_queue);
+  stage_flat(sc, fr);
+  WaveIO io{w, in_queue ? w.queue[parity] : nullptr, 0, seed_lo, seed_hi, false};
+  traverse_flat(sc, fr, io, count, &w.ctl->cursor_traverse);
+}
+
+template <bool COUNT, bool MEDIA, int NODES>
+__global__ void __launch_bounds__(128, (COUNT || MEDIA || NODES == NODES_WIDE) ? 1 : RTW_TRAVERSE_MINBLOCKS)
+    k_wave_traverse(SceneDev sc, WaveDev w, uint32_t parity, uint32_t seed_lo, uint32_t seed_hi) {
+  WaveCtl* ctl = w.ctl;
+  uint32_t count, in_queue;
+  traverse_prologue(w, parity, count, in_queue);
   const uint32_t lane = threadIdx.x & 31;
   TraverseCounters cnt;
   WaveIO io{w, in_queue ? w.queue[parity] : nullptr, 0, seed_lo, seed_hi, false};
@@ -641,7 +660,8 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
     int nb = 0;
     const void* kernels[TK_N] = {(const void*)k_wave_traverse<false, false, NODES_PAIR>, (const void*)k_wave_traverse<false, true, NODES_PAIR>,
                                  (const void*)k_wave_traverse<false, false, NODES_WIDE>, (const void*)k_wave_traverse<false, false, NODES_COMPACT>,
-                                 (const void*)k_wave_traverse<true, true, NODES_PAIR>, (const void*)k_wave_traverse<true, true, NODES_COMPACT>};
+                                 (const void*)k_wave_traverse<true, true, NODES_PAIR>, (const void*)k_wave_traverse<true, true, NODES_COMPACT>,
+                                 (const void*)k_wave_traverse_flat};
     for (int k = 0; k < TK_N; ++k) {
       RTW_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernels[k], 128, 0));
       wh->blocks_trav[k] = std::max(nb, 1) * s->num_sms;
@@ -680,8 +700,11 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
   const bool time_kernels = (p->flags & 2u) != 0;
   // compact pairs exist only when rtw_build found the hierarchy too large for the caches (rtw_bvh.cu)
   const bool compact = s->dev.nodes_c != nullptr && !s->dev.has_media;
+  // a scene that is one leaf (<= 32 primitives, no media) is not walked at all (RTW_FLAT=0: use the general kernel)
+  bool flat = s->dev.flat_count > 0 && !s->dev.has_media;
+  if (const char* e = getenv("RTW_FLAT")) flat = flat && atoi(e) != 0;
   const TravKind kind = count_trav ? (compact ? TK_COUNT_COMPACT : TK_COUNT)
-                                   : (s->dev.has_media ? TK_MEDIA : (compact ? TK_COMPACT : (wide ? TK_WIDE : TK_PAIR)));
+                                   : (s->dev.has_media ? TK_MEDIA : (flat ? TK_FLAT : (compact ? TK_COMPACT : (wide ? TK_WIDE : TK_PAIR))));
   auto launch_traverse = [&](cudaStream_t sk, const WaveDev& wd, uint32_t parity, int grid) {
     switch (kind) {
       case TK_PAIR: k_wave_traverse<false, false, NODES_PAIR><<<grid, 128, 0, sk>>>(s->dev, wd, parity, f.seed_lo, f.seed_hi); break;
@@ -689,6 +712,7 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
       case TK_WIDE: k_wave_traverse<false, false, NODES_WIDE><<<grid, 128, 0, sk>>>(s->dev, wd, parity, f.seed_lo, f.seed_hi); break;
       case TK_COMPACT: k_wave_traverse<false, false, NODES_COMPACT><<<grid, 128, 0, sk>>>(s->dev, wd, parity, f.seed_lo, f.seed_hi); break;
       case TK_COUNT: k_wave_traverse<true, true, NODES_PAIR><<<grid, 128, 0, sk>>>(s->dev, wd, parity, f.seed_lo, f.seed_hi); break;
+      case TK_FLAT: k_wave_traverse_flat<<<grid, 128, 0, sk>>>(s->dev, wd, parity, f.seed_lo, f.seed_hi); break;
       default: k_wave_traverse<true, true, NODES_COMPACT><<<grid, 128, 0, sk>>>(s->dev, wd, parity, f.seed_lo, f.seed_hi); break;
     }
   };

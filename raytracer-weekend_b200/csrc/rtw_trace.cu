@@ -66,6 +66,15 @@ __global__ void __launch_bounds__(128) k_trace_bvh(SceneDev sc, const rtw_ray* _
 #endif
 }
 
+// flat scenes (one leaf of <= 32 primitives): the same kernel body the wavefront renderer runs for them
+__global__ void __launch_bounds__(128) k_trace_flat(SceneDev sc, const rtw_ray* __restrict__ rays, uint32_t n,
+                                                    rtw_hit* __restrict__ hits, uint32_t* cursor) {
+  __shared__ FlatRecords fr;
+  stage_flat(sc, fr);
+  BatchIO io{sc, rays, hits};
+  traverse_flat(sc, fr, io, n, cursor);
+}
+
 __global__ void __launch_bounds__(128) k_trace_brute(SceneDev sc, const rtw_ray* __restrict__ rays, uint64_t n,
                                                      rtw_hit* __restrict__ hits) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -98,6 +107,8 @@ int trace_closest_device(rtw_scene* s, const rtw_ray* d_rays, uint64_t n, rtw_hi
     bool wide = false;
     if (const char* e = getenv("RTW_WIDE"))
       wide = atoi(e) != 0 && !s->dev.has_media && 3u * (s->bvh_height / 2u + 1u) + 2u <= RTW_STACK_SIZE;
+    bool flat = s->dev.flat_count > 0 && !s->dev.has_media;
+    if (const char* e = getenv("RTW_FLAT")) flat = flat && atoi(e) != 0;
     uint32_t* cursor = nullptr;
     RTW_CUDA_TRY(cudaMallocAsync((void**)&cursor, sizeof(uint32_t), st));
     for (uint64_t done = 0; done < n;) {
@@ -106,6 +117,8 @@ int trace_closest_device(rtw_scene* s, const rtw_ray* d_rays, uint64_t n, rtw_hi
       uint32_t grid = (uint32_t)std::min<uint64_t>((uint64_t)blocks_per_sm * s->num_sms, (chunk + T - 1) / T);
       if (s->dev.has_media)
         k_trace_bvh<true, NODES_PAIR><<<grid, T, 0, st>>>(s->dev, d_rays + done, chunk, d_hits + done, cursor);
+      else if (flat)
+        k_trace_flat<<<grid, T, 0, st>>>(s->dev, d_rays + done, chunk, d_hits + done, cursor);
       else if (s->dev.nodes_c)  // hierarchy beyond the caches: compact pairs (rtw_bvh.cu)
         k_trace_bvh<false, NODES_COMPACT><<<grid, T, 0, st>>>(s->dev, d_rays + done, chunk, d_hits + done, cursor);
       else if (wide)

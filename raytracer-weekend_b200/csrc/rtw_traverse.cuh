@@ -474,6 +474,80 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
   }
 }
 
+// Flat scenes (SceneDev::flat_count > 0: at most 32 primitives in one leaf, e.g. the Cornell box): every ray tests
+// every primitive, in the same order — there is nothing to walk and nothing to balance.  The primitive records are
+// staged in shared memory once per block (48 B geometry + meta + canonical id), the loop over them is warp-uniform
+// (broadcast LDS, no per-lane addressing, uniform type / instance branches) and a warp simply takes 32 rays at a
+// time.  Same tests, same order of the float operations, same tie rule as traverse_persistent.
+struct FlatRecords {
+  float4 g[32][3];
+  uint32_t meta[32];
+  int32_t prim[32];
+};
+
+__device__ __forceinline__ void stage_flat(const SceneDev& sc, FlatRecords& fr) {
+  for (uint32_t i = threadIdx.x; i < sc.flat_count; i += blockDim.x) {
+    fr.g[i][0] = sc.geom[3 * (size_t)i]; fr.g[i][1] = sc.geom[3 * (size_t)i + 1]; fr.g[i][2] = sc.geom[3 * (size_t)i + 2];
+    fr.meta[i] = sc.slot_meta[i];
+    fr.prim[i] = sc.slot_prim[i];
+  }
+  __syncthreads();
+}
+
+template <class IO>
+__device__ __forceinline__ void traverse_flat(const SceneDev& sc, const FlatRecords& fr, IO& io, uint32_t count, uint32_t* cursor) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t nprim = sc.flat_count;
+  for (;;) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(cursor, 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= count) break;
+    const uint32_t index = base + lane;
+    v3 o = mk(0, 0, 0), d = mk(0, 0, 1);
+    float time = 0.f, t_min = 0.f, best_t = 0.f;
+    int32_t slot0 = -1;
+    bool resumed = false;
+    const bool active = index < count && io.load(index, o, d, time, t_min, best_t, slot0, resumed);
+    int32_t best_slot = -1, best_id = -2;
+    uint32_t best_meta = 0, cur_inst = 0;
+    v3 oi = o, di = d;
+    for (uint32_t k = 0; k < nprim; ++k) {  // warp-uniform
+      const uint32_t pm = fr.meta[k];
+      const uint32_t type = pm & 7u, inst = pm >> RTW_META_TYPE_BITS;
+      if (inst != cur_inst) {
+        oi = o; di = d;
+        if (inst != 0) ray_to_instance(sc, inst, oi, di);
+        cur_inst = inst;
+      }
+      const float4 g0 = fr.g[k][0];
+      float t, a, b;
+      bool hit;
+      if (type == PT_RECT_XZ)
+        hit = rect_t_perm(oi.x, oi.z, oi.y, di.x, di.z, di.y, t_min, best_t, g0, fr.g[k][1].x, t);
+      else if (type == PT_RECT_XY)
+        hit = rect_t_perm(oi.x, oi.y, oi.z, di.x, di.y, di.z, t_min, best_t, g0, fr.g[k][1].x, t);
+      else if (type == PT_RECT_YZ)
+        hit = rect_t_perm(oi.y, oi.z, oi.x, di.y, di.z, di.x, t_min, best_t, g0, fr.g[k][1].x, t);
+      else if (type <= PT_MSPHERE) {
+        v3 center = mk(g0.x, g0.y, g0.z);
+        if (type == PT_MSPHERE) center = moving_center(g0, fr.g[k][1], fr.g[k][2], time);
+        hit = sphere_t(oi, di, t_min, best_t, center, g0.w, t);
+      } else {
+        hit = tri_t(oi, di, t_min, best_t, g0, fr.g[k][1], fr.g[k][2], t, a, b);
+      }
+      if (hit && active) {
+        if (best_slot < 0 || t < best_t) {
+          best_t = t; best_slot = (int32_t)k; best_meta = pm; best_id = fr.prim[k];
+        } else if (fr.prim[k] > best_id) {  // t == best_t: the later primitive of the canonical order wins
+          best_slot = (int32_t)k; best_meta = pm; best_id = fr.prim[k];
+        }
+      }
+    }
+    if (active) io.store(index, o, d, time, best_slot, best_t, best_meta);
+  }
+}
+
 // Every primitive in canonical order: hittable/mod.rs:57-69 literally (closest_so_far shrink,
 // later primitive wins on equal t).  The debug / ground-truth path of rtw_trace_closest.
 __device__ __forceinline__ void brute_closest(const SceneDev& sc, v3 o, v3 d, float time, float t_min, float t_max,

@@ -314,12 +314,13 @@ def test_tail_of_the_frame_switches_to_queues_and_stays_bit_exact(gpu, oracle):
             assert np.array_equal(bits(ag), bits(ao)), (w, h, spp, pool)
 
 
-@pytest.mark.parametrize("env,record_bytes", [("RTW_COMPACT", 32.0), ("RTW_WIDE", 128.0)])
-def test_alternative_node_records_keep_parity(gpu, oracle, monkeypatch, env, record_bytes):
+@pytest.mark.parametrize("env,value,record_bytes", [("RTW_COMPACT", "1", 32.0), ("RTW_WIDE", "1", 128.0), ("RTW_FLAT", "0", 64.0)])
+def test_alternative_node_records_keep_parity(gpu, oracle, monkeypatch, env, value, record_bytes):
     """Compact 32-byte pairs (16-bit boxes on the scene grid; what rtw_build picks for >= 2^20 primitives) and the
     experimental 4-wide walk, forced on for small scenes: closest hits and images stay what the oracle says — the
-    quantised boxes contain the exact ones, so culling stays conservative."""
-    monkeypatch.setenv(env, "1")     # read by rtw_build (compact) / rtw_render, rtw_trace_closest (wide)
+    quantised boxes contain the exact ones, so culling stays conservative.  RTW_FLAT=0: one-leaf scenes through the
+    general kernel instead of the flat-scene kernel they normally take."""
+    monkeypatch.setenv(env, value)   # read by rtw_build (compact) / rtw_render, rtw_trace_closest (wide, flat)
     for scene, aspect in (("cow-lambert-metal", 16 / 9), ("stress:3000:400", 16 / 9), ("cornell-box", 1.0)):
         with rtw.Scene.from_name(gpu, scene, aspect, seed=3) as sg, rtw.Scene.from_name(oracle, scene, aspect, seed=3) as so:
             cam = sg.cameras[0]
