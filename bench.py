@@ -325,7 +325,7 @@ def main():
             if tj:  # ncu dram__bytes_read.sum + dram__bytes_write.sum per segment, scaled to this run's launch size
                 traffic = tj["dram_bytes_per_segment"] * seg_per_launch
         resident = pairs_per_seg < 64 and scene.build_stats.device_bytes < (100 << 20)
-        roofline = {"bound": "hbm", "kernel": "k_wave_traverse", "achieved": ach, "peak": peak, "unit": "GB/s",
+        roofline = {"bound": "hbm", "kernel": "k_wave_traverse_flat" if scene.num_prims <= 32 else "k_wave_traverse", "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                     "bytes_per_launch": bytes_per_seg * seg_per_launch,
                     "bytes_per_segment": bytes_per_seg, "pairs_per_segment": pairs_per_seg, "node_record_bytes": node_bytes,
