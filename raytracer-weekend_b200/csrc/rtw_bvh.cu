@@ -643,6 +643,7 @@ int build_scene_device(rtw_scene* s, float time0, float time1, rtw_build_stats* 
   d.num_prims = n;
   d.num_nodes = n > 1 ? n - 1 : 1;
   d.has_instances = s->inst_range.size() > 1 ? 1u : 0u;
+  d.has_tri_shade = s->tri_shade.empty() ? 0u : 1u;
   d.has_media = 0;
   for (uint32_t m : s->prim_meta)
     if ((m & 7u) >= PT_MEDIUM_SPHERE) { d.has_media = 1; break; }

@@ -30,6 +30,9 @@ namespace rtw {
 namespace {
 
 #define RTW_MAX_SUBPOOLS 4
+#ifndef RTW_WIDE_HIT
+#define RTW_WIDE_HIT 0  // A/B r01: 16-byte hit record (meta + material): shade +-0, traversal +1-2 % slower
+#endif
 // ray_d.w of a slot: 0 = a live ray, else
 #define RTW_SLOT_DEAD 1.0f     // no work left for the slot (end of the frame, identity mode)
 #define RTW_SLOT_PENDING 2.0f  // traversal suspended in the drain of the last launch (rtw_traverse.cuh)
@@ -52,7 +55,12 @@ struct WaveCtl {           // one per sub-pool (+ one extra whose item_cursor is
 struct WaveDev {
   float4* ray_o;    // origin.xyz, time
   float4* ray_d;    // direction.xyz, -
+#if RTW_WIDE_HIT
+  int4* hit;        // primitive slot (or -1), t bits, slot meta (type | inst << 3), material: what the shade kernel
+                    // would otherwise fetch through the slot in a dependent load
+#else
   int2* hit;        // primitive slot (or -1), t bits
+#endif
   float4* thr;      // throughput T.rgb
   float4* sum;      // running slice sum rgb
   uint4* state;     // pixel index (row*w+col), sample, sample_end, bounce | slice << 8
@@ -238,6 +246,7 @@ struct WaveIO {
 #endif
   static constexpr int kSuspendLanes = RTW_SUSPEND_LANES;
   bool was_pending;
+  const int2* __restrict__ slot_ms;  // SceneDev::slot_ms
   __device__ __forceinline__ bool load(uint32_t i, v3& o, v3& d, float& time, float& t_min, float& t_max, int32_t& slot0,
                                        bool& resumed) {
     slot = queue ? queue[i] : w.slot_base + i;
@@ -247,17 +256,25 @@ struct WaveIO {
     t_min = 0.001f; t_max = __int_as_float(0x7f800000);  // lib.rs:102: world.hit(r, 0.001, f32::INFINITY)
     resumed = was_pending = d4.w == RTW_SLOT_PENDING;
     if (resumed) {  // suspended by the previous launch with this hit
-      const int2 h = w.hit[slot];
+      const auto h = w.hit[slot];
       slot0 = h.x; t_max = __int_as_float(h.y);
     }
     return true;
   }
-  __device__ __forceinline__ void store(uint32_t, v3, v3 d, float, int32_t hslot, float t, uint32_t) {
+  __device__ __forceinline__ void store(uint32_t, v3, v3 d, float, int32_t hslot, float t, uint32_t meta) {
+#if RTW_WIDE_HIT
+    w.hit[slot] = make_int4(hslot, __float_as_int(t), (int)meta, hslot >= 0 ? slot_ms[hslot].x : 0);
+#else
     w.hit[slot] = make_int2(hslot, __float_as_int(t));
+#endif
     if (was_pending) w.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.f);
   }
   __device__ __forceinline__ void suspend(uint32_t, int32_t hslot, float t) {
+#if RTW_WIDE_HIT
+    w.hit[slot] = make_int4(hslot, __float_as_int(t), 0, 0);
+#else
     w.hit[slot] = make_int2(hslot, __float_as_int(t));
+#endif
     const float4 d4 = w.ray_d[slot];
     w.ray_d[slot] = make_float4(d4.x, d4.y, d4.z, RTW_SLOT_PENDING);
   }
@@ -290,7 +307,7 @@ __global__ void __launch_bounds__(128, 8) k_wave_traverse_flat(SceneDev sc, Wave
   uint32_t count, in_queue;
   traverse_prologue(w, parity, count, in_queue);
   stage_flat(sc, fr);
-  WaveIO io{w, in_queue ? w.queue[parity] : nullptr, 0, seed_lo, seed_hi, false};
+  WaveIO io{w, in_queue ? w.queue[parity] : nullptr, 0, seed_lo, seed_hi, false, sc.slot_ms};
   traverse_flat(sc, fr, io, count, &w.ctl->cursor_traverse);
 }
 
@@ -302,7 +319,7 @@ __global__ void __launch_bounds__(128, (COUNT || MEDIA || NODES == NODES_WIDE) ?
   traverse_prologue(w, parity, count, in_queue);
   const uint32_t lane = threadIdx.x & 31;
   TraverseCounters cnt;
-  WaveIO io{w, in_queue ? w.queue[parity] : nullptr, 0, seed_lo, seed_hi, false};
+  WaveIO io{w, in_queue ? w.queue[parity] : nullptr, 0, seed_lo, seed_hi, false, sc.slot_ms};
 #if RTW_TOP_TREE > 0
   __shared__ float4 top_smem[4 * RTW_TOP_TREE];
   stage_top_tree(sc, top_smem);
@@ -406,7 +423,11 @@ __global__ void __launch_bounds__(128) k_wave_shade(
     Item it;
     it.pixel = it.sample = it.sample_end = it.slice = 0;
     float4 o4, d4, T4, s4;
+#if RTW_WIDE_HIT
+    int4 h;
+#else
     int2 h;
+#endif
     uint4 st;
     if (active) {  // every load of the slot's state is issued before the first use
       slot = queue ? queue[i] : w.slot_base + i;
@@ -427,9 +448,17 @@ __global__ void __launch_bounds__(128) k_wave_shade(
         L = T * f.background;
         ended = true;
       } else {
+#if RTW_WIDE_HIT
+        const uint32_t meta = (uint32_t)h.z;
+        const MaterialRec m = sc.materials[h.w];
+        // only a triangle with per-vertex normals / uvs needs its TriShade index (one more hop through the slot)
+        int2 ms = make_int2(h.w, -1);
+        if ((meta & 7u) == PT_TRI && sc.has_tri_shade) ms.y = sc.slot_ms[h.x].y;
+#else
         const uint32_t meta = sc.slot_meta[h.x];
         const int2 ms = sc.slot_ms[h.x];
         const MaterialRec m = sc.materials[ms.x];
+#endif
         const v3 o = mk(o4.x, o4.y, o4.z), d = mk(d4.x, d4.y, d4.z);
         const bool need_uv = !m.solid && (m.type == MT_LAMBERTIAN || m.type == MT_DIFFUSE_LIGHT) && texture_needs_uv(sc, m.tex);
         HitRec rec;
