@@ -340,3 +340,19 @@ def test_alternative_node_records_keep_parity(gpu, oracle, monkeypatch, env, val
             if scene == "cornell-box":
                 ao, sto = so.render(cam, so.params(64, 36, 3, seed=5, slices=1))
                 assert np.array_equal(bits(ag), bits(ao)) and stg.segments == sto.segments
+
+
+def test_trace_parity_on_a_million_ray_batches(gpu, oracle):
+    """1 M camera rays + 1 M second-bounce rays captured from the oracle, closest hits through
+    rtw_trace_closest against the oracle's canonical-order flat list: ids / t / p / normal bit for bit, uv 1e-5."""
+    with rtw.Scene.from_name(gpu, "cow-lambert-metal", 16 / 9, seed=3) as sg, \
+            rtw.Scene.from_name(oracle, "cow-lambert-metal", 16 / 9, seed=3) as so:
+        cam = sg.cameras[0]
+        for bounce in (0, 1):
+            rays = oracle.capture_rays(so, cam, 1366, 768, 2024, 0, bounce)          # 1 049 088 rays
+            assert len(rays) > 1_000_000
+            hg, ho = sg.trace_closest(rays), so.trace_closest(rays)
+            assert (ho["prim_id"] >= 0).sum() > (100_000 if bounce == 0 else 20_000)   # ended paths yield null rays
+            assert_hits_equal(hg, ho, f"cow, 1M rays, bounce {bounce}")
+            brute = sg.trace_closest(rays[:50_000], mode=rtw.RTW_TRACE_BRUTE)          # the GPU's own flat list
+            assert np.array_equal(brute["prim_id"], hg["prim_id"][:50_000]) and np.array_equal(bits(brute["t"]), bits(hg["t"][:50_000]))
