@@ -23,4 +23,4 @@ for env in ({}, {"RTW_COMPACT": "1"}, {"RTW_WIDE": "1"}, {"RTW_FLAT": "0"}):
             s.render_frames([cam, cam], s.params(16, 16, 1, seed=1), lambda i, a, st: True)
     for k in env:
         del os.environ[k]
-print("sanitize_smoke: all variants ran")
+print("variants_smoke: all variants ran")
