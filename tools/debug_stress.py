@@ -1,9 +1,7 @@
 import sys, time
 import numpy as np
 sys.path.insert(0, ".")
-sys.path.insert(0, "tests")
 import raytracer_weekend_b200 as rtw
-from conftest import Oracle
 name = sys.argv[1] if len(sys.argv) > 1 else "stress:1000000:1000000"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 gpu = rtw.cuda_backend()
@@ -19,9 +17,5 @@ print("mismatches", len(bad), "of", n)
 for i in bad[:10]:
     print(i, "brute", hb["prim_id"][i], hb["t"][i], "bvh", hv["prim_id"][i], hv["t"][i], "types", s.prim_info(int(hb["prim_id"][i])) if hb["prim_id"][i] >= 0 else None,
           s.prim_info(int(hv["prim_id"][i])) if hv["prim_id"][i] >= 0 else None)
-if len(bad):
-    orc = Oracle()
-    so = rtw.Scene.from_name(orc, name, 16/9, seed=2024)
-    ho = so.trace_closest(rays[bad[:10]])
-    for k, i in enumerate(bad[:10]):
-        print(i, "oracle", ho["prim_id"][k], ho["t"][k])
+# (the CPU oracle is test infrastructure: to see what it says about these rays use tests/, e.g.
+#  test_large_scene_mismatches_are_only_ill_conditioned_reference_hits)
