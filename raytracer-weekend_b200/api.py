@@ -205,6 +205,7 @@ def host_lib():
         h.rtwh_perlin_new.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         h.rtwh_load_obj.argtypes = [C.c_char_p, C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        h.rtwh_open_image.argtypes = [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_void_p, C.c_size_t]
         h.rtwh_parse_obj.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
         h.rtwh_parse_obj.restype = C.c_longlong
         h.rtwh_progress_image_start.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t]
@@ -217,6 +218,18 @@ def host_lib():
         h.rtwh_set_asset_dir(ASSET_DIR.encode())
         _host_lib = h
     return _host_lib
+
+
+def open_image(path: str) -> np.ndarray:
+    """ImageTexture::open (image_texture.rs:23-30) of the host front end: the decoded RGB8 texels [h, w, 3]."""
+    w, hgt = C.c_uint32(), C.c_uint32()
+    hl = host_lib()
+    if hl.rtwh_open_image(path.encode(), C.byref(w), C.byref(hgt), None, 0) < 0:
+        raise RtwError(hl.rtwh_capi_error().decode())
+    out = np.zeros((hgt.value, w.value, 3), np.uint8)
+    if hl.rtwh_open_image(path.encode(), C.byref(w), C.byref(hgt), out.ctypes.data, out.size) < 0:
+        raise RtwError(hl.rtwh_capi_error().decode())
+    return out
 
 
 def parse_obj(path: str, mode: int = 0, threads: int = 0):

@@ -140,6 +140,23 @@ int rtwh_load_obj(const char* path, uint32_t* ntris, float* verts, float* normal
   }
 }
 
+// ImageTexture::open (image_texture.rs:23-30) as the scenes use it: registry, PNG decoder, .rtwi / .ppm.  Call with
+// rgb8 == NULL to size the buffer (width * height * 3 bytes, row 0 = top).
+int rtwh_open_image(const char* path, uint32_t* width, uint32_t* height, uint8_t* rgb8, size_t cap) {
+  if (!path || !width || !height) return fail(RTW_ERR_INVALID, "open_image: NULL argument");
+  try {
+    auto t = rtwh::ImageTexture::open(path);
+    *width = t->width(); *height = t->height();
+    if (rgb8) {
+      if (cap < t->rgb().size()) return fail(RTW_ERR_INVALID, "open_image: buffer too small");
+      memcpy(rgb8, t->rgb().data(), t->rgb().size());
+    }
+    return RTW_OK;
+  } catch (const std::exception& e) {
+    return fail(RTW_ERR_INVALID, e.what());
+  }
+}
+
 // OBJ ingest check / benchmark: parse `path` with the parallel parser (mode 0, `threads` <= 0: all) or with the
 // single-threaded reference parser (mode 1).  Returns the triangle count; checksum = FNV-1a over every output array
 // (positions, normals, uvs, presence flags, per-face material names), so two parses can be compared without moving

@@ -137,10 +137,12 @@ class ImageTexture : public Texture {  // image_texture.rs:17-51
  public:
   // decoded RGB8, row 0 = top
   ImageTexture(std::vector<uint8_t> rgb, uint32_t w, uint32_t h) : rgb_(std::move(rgb)), w_(w), h_(h) {}
-  // ImageTexture::open: resolves `path` through the asset registry, then .rtwi / .ppm files
+  // ImageTexture::open: resolves `path` through the asset registry, then decodes a PNG file (lossless: the texels
+  // are exactly the reference decoder's), then .rtwi / .ppm files with pre-decoded pixels
   static std::shared_ptr<ImageTexture> open(const std::string& path);
   uint32_t width() const { return w_; }
   uint32_t height() const { return h_; }
+  const std::vector<uint8_t>& rgb() const { return rgb_; }
 
  protected:
   int emit(Flattener& f) const override;

@@ -289,3 +289,109 @@ def test_parallel_obj_parser_on_the_reference_models(stem):
     ref = rtw.parse_obj(f"{REF_MODELS}/{stem}.obj", mode=1)
     for threads in (1, 0):
         assert rtw.parse_obj(f"{REF_MODELS}/{stem}.obj", mode=0, threads=threads)[:2] == ref[:2]
+
+
+# ---- PNG textures (image_texture.rs:23-30): lossless, so the decoder must reproduce the pixels exactly ---------------
+def _png_bytes(img: np.ndarray, color_type: int, depth: int = 8, palette=None, filters=(0, 1, 2, 3, 4)) -> bytes:
+    """A PNG written by hand so that every scanline filter type occurs (PIL picks filters by heuristics)."""
+    import struct
+    import zlib
+
+    h, w = img.shape[:2]
+    rows = img.reshape(h, -1).astype(np.uint8)
+    if depth < 8:                                   # pack `depth`-bit samples MSB first
+        per = 8 // depth
+        padded = np.zeros((h, (w + per - 1) // per * per), np.uint8)
+        padded[:, :w] = rows
+        rows = sum(padded[:, k::per].astype(np.uint16) << (8 - depth * (k + 1)) for k in range(per)).astype(np.uint8)
+    bpp = max(1, rows.shape[1] * 8 // w // 8) if depth == 8 else 1
+    out, prev = bytearray(), np.zeros(rows.shape[1], np.int32)
+    for y in range(h):
+        cur = rows[y].astype(np.int32)
+        a = np.concatenate([np.zeros(bpp, np.int32), cur[:-bpp]])
+        c = np.concatenate([np.zeros(bpp, np.int32), prev[:-bpp]])
+        ft = filters[y % len(filters)]
+        if ft == 0:
+            pred = 0
+        elif ft == 1:
+            pred = a
+        elif ft == 2:
+            pred = prev
+        elif ft == 3:
+            pred = (a + prev) // 2
+        else:
+            p = a + prev - c
+            pa, pb, pc = abs(p - a), abs(p - prev), abs(p - c)
+            pred = np.where((pa <= pb) & (pa <= pc), a, np.where(pb <= pc, prev, c))
+        out.append(ft)
+        out += ((cur - pred) & 255).astype(np.uint8).tobytes()
+        prev = cur
+
+    def chunk(tag, data):
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+
+    png = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, color_type, 0, 0, 0))
+    if palette is not None:
+        png += chunk(b"PLTE", np.asarray(palette, np.uint8).tobytes())
+    data = zlib.compress(bytes(out), 6)
+    return png + chunk(b"IDAT", data[:len(data) // 2]) + chunk(b"IDAT", data[len(data) // 2:]) + chunk(b"IEND", b"")
+
+
+def test_png_decoder_reproduces_every_supported_layout(tmp_path):
+    rs = np.random.RandomState(11)
+    w, h = 37, 23
+    rgb = rs.randint(0, 256, (h, w, 3)).astype(np.uint8)
+    rgba = np.concatenate([rgb, rs.randint(0, 256, (h, w, 1)).astype(np.uint8)], axis=2)
+    grey = rs.randint(0, 256, (h, w)).astype(np.uint8)
+    ga = np.stack([grey, rs.randint(0, 256, (h, w)).astype(np.uint8)], axis=2)
+    pal = rs.randint(0, 256, (200, 3)).astype(np.uint8)
+    idx = rs.randint(0, 200, (h, w)).astype(np.uint8)
+    cases = {
+        "rgb": (_png_bytes(rgb, 2), rgb),
+        "rgba": (_png_bytes(rgba, 6), rgb),                                  # alpha dropped (image_texture.rs:44-50)
+        "grey": (_png_bytes(grey, 0), np.repeat(grey[:, :, None], 3, 2)),
+        "grey_alpha": (_png_bytes(ga, 4), np.repeat(grey[:, :, None], 3, 2)),
+        "palette": (_png_bytes(idx, 3, palette=pal), pal[idx]),
+        "grey4": (_png_bytes(grey >> 4, 0, depth=4), np.repeat(((grey >> 4) * 17)[:, :, None], 3, 2)),
+        "grey1": (_png_bytes(grey >> 7, 0, depth=1), np.repeat(((grey >> 7) * 255)[:, :, None], 3, 2)),
+        "palette2": (_png_bytes(idx & 3, 3, depth=2, palette=pal[:4]), pal[idx & 3]),
+    }
+    for name, (data, want) in cases.items():
+        p = tmp_path / f"{name}.png"
+        p.write_bytes(data)
+        got = rtw.open_image(str(p))
+        assert got.shape == want.shape and np.array_equal(got, want), name
+    # files written by an independent encoder, decoded by an independent decoder
+    from PIL import Image
+    for mode, arr in (("RGB", rgb), ("RGBA", rgba), ("L", grey), ("P", idx)):
+        im = Image.fromarray(arr, mode)
+        if mode == "P":
+            im.putpalette(pal.tobytes())
+        p = tmp_path / f"pil_{mode}.png"
+        im.save(p, optimize=(mode == "RGB"))
+        assert np.array_equal(rtw.open_image(str(p)), np.asarray(Image.open(p).convert("RGB"))), mode
+
+
+def test_png_decoder_refuses_what_it_cannot_reproduce(tmp_path):
+    import struct
+    rgb = np.zeros((4, 4, 3), np.uint8)
+    good = _png_bytes(rgb, 2)
+    p = tmp_path / "x.png"
+    p.write_bytes(good[:-20])
+    with pytest.raises(rtw.RtwError, match="truncated|CRC|IDAT"):
+        rtw.open_image(str(p))
+    bad = bytearray(good)
+    bad[40] ^= 0xFF                                                          # corrupt the IDAT payload: CRC check
+    p.write_bytes(bytes(bad))
+    with pytest.raises(rtw.RtwError, match="CRC"):
+        rtw.open_image(str(p))
+    ihdr16 = good.replace(struct.pack(">IIBBBBB", 4, 4, 8, 2, 0, 0, 0), struct.pack(">IIBBBBB", 4, 4, 16, 2, 0, 0, 0))
+    p.write_bytes(ihdr16)
+    with pytest.raises(rtw.RtwError, match="CRC|bit depth"):                 # (the IHDR CRC no longer matches either)
+        rtw.open_image(str(p))
+    from PIL import Image
+    Image.fromarray(np.arange(64, dtype=np.uint16).reshape(8, 8) * 900).save(tmp_path / "g16.png")      # 16-bit grey
+    with pytest.raises(rtw.RtwError, match="bit depth 16"):
+        rtw.open_image(str(tmp_path / "g16.png"))
+    with pytest.raises(rtw.RtwError, match="no decoded image"):              # JPEG stays a pre-decoded asset
+        rtw.open_image(str(tmp_path / "nothing.jpg"))
