@@ -457,3 +457,20 @@ def test_oracle_matches_committed_golden(oracle):
             assert np.array_equal(hits["prim_id"], want["prim_id"])
             assert np.array_equal(bits(hits["t"]), bits(want["t"]))
             assert np.array_equal(bits(hits["normal"]), bits(want["normal"]))
+
+
+RENDER_GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "oracle_renders_v1.npz")
+
+
+def test_oracle_matches_committed_render_golden(oracle):
+    """tests/golden/make_golden_renders.py: small frames of seven scenes (every material, texture, wrapper, the media).
+    Pins integrator, materials, textures and the Philox stream of the oracle bit for bit."""
+    g = np.load(RENDER_GOLDEN)
+    scenes = sorted({k.split("/")[0] for k in g.files})
+    assert len(scenes) == 7
+    for scene in scenes:
+        w, h, spp, slices, segments = (int(x) for x in g[f"{scene}/meta"])
+        with rtw.Scene.from_name(oracle, scene, w / h, seed=1) as s:
+            accum, st = s.render(s.cameras[0], s.params(w, h, spp, seed=4242, slices=slices))
+        assert st.segments == segments, scene
+        assert np.array_equal(bits(accum), bits(g[f"{scene}/accum"])), scene
