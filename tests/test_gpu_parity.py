@@ -380,3 +380,41 @@ def test_render_against_committed_golden_frames(gpu):
         print(f"{scene}: rmse / mean = {rmse / float(np.mean(want)):.5f}, identical pixels = {same:.4f}")
         assert rmse <= 0.05 * float(np.mean(want)) + 1e-6, (scene, rmse)
         assert same >= 0.93, (scene, same)
+
+
+def test_console_app_backend_cuda_end_to_end(gpu, tmp_path):
+    """console_app (main.rs:28-95 mirror) with --backend cuda: PNG per camera through rtw_render_frames, identical to
+    a direct render + the reference tonemap; the --progress-out stream decodes to the same frame (postcard + COBS)."""
+    import os
+    import struct
+    import subprocess
+    from PIL import Image
+    exe = os.path.join(rtw.PKG_DIR, "bin", "console_app")
+    out = tmp_path / "render"
+    prog = tmp_path / "progress.bin"
+    r = subprocess.run([exe, "-w", "48", "-a", "1.0", "-s", "5", "--seed", "9", "--backend", "cuda", "--out-dir", str(out),
+                        "--progress-out", str(prog), "cornell-box"], stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-1500:]
+    assert "1 frame(s)" in r.stderr
+    img = np.asarray(Image.open(out / "image_0000.png").convert("RGB"))
+    with rtw.Scene.from_name(gpu, "cornell-box", 1.0, seed=9) as s:
+        accum, _ = s.render(s.cameras[0], s.params(48, 48, 5, seed=9))
+        want = s.resolve_rgb8(accum, 5)
+    assert img.shape == (48, 48, 3) and np.array_equal(img, want)
+    frames = prog.read_bytes().split(b"\x00")
+    assert frames[-1] == b"" and len(frames) == 1 + 48 * 48 + 1 + 1
+
+    def cobs_decode(fr):
+        o, i = bytearray(), 0
+        while i < len(fr):
+            c = fr[i]
+            o += fr[i + 1:i + c]
+            i += c
+            if c != 0xFF and i < len(fr):
+                o.append(0)
+        return bytes(o)
+
+    assert cobs_decode(frames[0]) == bytes([0]) + struct.pack("<III", 48, 48, 5)
+    tag, row, col, red, green, blue = struct.unpack("<BIIfff", cobs_decode(frames[1]))
+    assert (tag, row, col) == (1, 47, 0) and np.array_equal(np.float32([red, green, blue]), accum[0, 0])
+    assert cobs_decode(frames[-2]) == bytes([2])
