@@ -815,8 +815,14 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
     if (!count_trav && !time_kernels) {
       // ---- product path: per sub-pool a CUDA graph of BATCH iterations, launched back to back; the host
       // looks at the live count of round i-1 while round i is already running.
-      const int BATCH = 16;  // even: the queue parity is back to 0 after every batch
-      int grid_t = wh->blocks_trav[kind], grid_s = wh->blocks_shade;
+      // BATCH is even (the queue parity is back to 0 after every batch).  The termination check lags one round, so a
+      // frame runs up to 2 x BATCH - 1 empty iterations at its end: 16 for long frames, 4 for short ones (fewer than
+      // two work items per slot: a ~50-iteration frame of a few ms, where 31 empty launch pairs would be a third of it).
+      const int BATCH = (f.n_items >= 2ull * pool) ? 16 : 4;
+      // a small pool does not need the full persistent grid: fewer blocks launch (and drain) faster
+      const int need_blocks = (int)((pool + 127u) / 128u);
+      int grid_t = std::min(wh->blocks_trav[kind], std::max(need_blocks, 1));
+      int grid_s = std::min(wh->blocks_shade, std::max(need_blocks, 1));
   
       cudaEvent_t ev_fork, ev_join[RTW_MAX_SUBPOOLS], ring_ev[RTW_MAX_SUBPOOLS][2];
       cudaGraph_t graph[RTW_MAX_SUBPOOLS];
