@@ -196,3 +196,30 @@ def test_rotation_from_stored_sin_cos_equals_rotation_from_angle(oracle):
     assert (hits[0]["prim_id"] >= 0).sum() > 50
     np.testing.assert_allclose(hits[0]["t"], hits[1]["t"], rtol=2e-6)      # numpy's sinf may differ from glibc's by an ulp
     assert np.array_equal(hits[0]["prim_id"], hits[1]["prim_id"])
+
+
+def test_bulk_triangle_ingest_and_unbuilt_scene_errors():
+    """rtw_add_triangles fills the scene arrays with all host threads from 2^16 triangles on: ids, types, instances and
+    per-face materials must be what the sequential path gives; render entry points refuse an unbuilt scene."""
+    b = rtw.cuda_backend()
+    rs = np.random.RandomState(2)
+    n = 70_000
+    verts = rs.uniform(-1, 1, (n, 9)).astype(np.float32)
+    with b.new_scene() as s:
+        mats = [s.lambertian_rgb(.1 * k, .2, .3) for k in range(5)]
+        ball = s.sphere((0, 0, 0), 1.0, mats[0])
+        s.push_translation((1, 2, 3))
+        mids = rs.randint(0, 5, n).astype(np.int32)
+        first = s.triangles(verts, mats[0], material_ids=np.asarray(mats, np.int32)[mids])
+        s.pop_transform()
+        small = s.triangles(verts[:10], mats[3])
+        assert (ball, first, small) == (0, 1, 1 + n) and s.num_prims == 1 + n + 10
+        for i in (0, 1, 12345, n - 1):
+            t, inst, m = s.prim_info(first + i)
+            assert (t, inst, m) == (5, 1, mats[mids[i]])          # triangle, inside the translation, its own material
+        assert s.prim_info(small + 9) == (5, 0, mats[3])
+        cam = rtw.camera_new((0, 0, -5), (0, 0, 0), (0, 1, 0), 40.0, 1.0)
+        with pytest.raises(rtw.RtwError, match="not built"):
+            s.render(cam, s.params(8, 8, 1))
+        with pytest.raises(rtw.RtwError, match="not built"):
+            s.render_frames([cam], s.params(8, 8, 1), lambda i, a, st: True)
