@@ -457,8 +457,9 @@ class Scene:
 
     def render_frames(self, cams, params: RenderParams, on_frame=None) -> int:
         """rtw_render_frames: frame i = cams[i], seed params.seed + i, over the resident scene.
-        on_frame(frame_no, accum[h, w, 3] (a copy), stats dict) -> truthy to continue; called in frame order on a
-        helper thread while the next frame renders.  Returns the number of frames delivered."""
+        on_frame(frame_no, accum[h, w, 3] (a copy), stats dict): return False to stop the animation (anything else,
+        including None, continues); called in frame order on a helper thread while the next frame renders.
+        Returns the number of frames delivered."""
         arr = (Camera * len(cams))(*cams)
         h, w = params.height, params.width
         errors = []
