@@ -395,3 +395,22 @@ def test_png_decoder_refuses_what_it_cannot_reproduce(tmp_path):
         rtw.open_image(str(tmp_path / "g16.png"))
     with pytest.raises(rtw.RtwError, match="no decoded image"):              # JPEG stays a pre-decoded asset
         rtw.open_image(str(tmp_path / "nothing.jpg"))
+
+
+def test_progress_stream_through_the_receiver_stand_in():
+    """tools/progress_receiver.py restates discovery_host_receiver/src/main.rs:56-101 (tonemap per pixel, put_pixel(column,
+    row), rotate180 at ImageEnd).  Pixel.row counts from the bottom (lib.rs:58), so after the rotation the receiver's
+    image is the frame mirrored left-right — the same thing it shows for the embedded renderer."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("progress_receiver", os.path.join(ROOT, "tools", "progress_receiver.py"))
+    recv = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(recv)
+    rs = np.random.RandomState(8)
+    h, w, spp = 6, 9, 4
+    accum = rs.uniform(0, 6, (h, w, 3)).astype(np.float32)
+    frames = list(recv.receive(rtw.progress_frame(accum, spp) + rtw.progress_frame(accum * 0.5, spp)))
+    assert len(frames) == 2 and frames[0].shape == (h, w, 3)
+    c = np.clip(np.sqrt(accum * np.float32(1.0 / spp)), 0, np.float32(0.999))
+    top_down = (np.float32(255.999) * c).astype(np.uint8)        # the frame as console_app writes it (main.rs:66-90)
+    # receiver: y = Pixel.row = h-1-y_top, then rotate180 -> y_top, x mirrored
+    assert np.array_equal(frames[0], top_down[:, ::-1])
