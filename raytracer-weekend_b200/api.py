@@ -205,6 +205,12 @@ def host_lib():
         h.rtwh_perlin_new.argtypes = [C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         h.rtwh_load_obj.argtypes = [C.c_char_p, C.POINTER(C.c_uint32), C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        h.rtwh_world_create.argtypes = [C.c_char_p, C.c_float, C.c_uint64]
+        h.rtwh_world_create.restype = C.c_void_p
+        h.rtwh_world_destroy.argtypes = [C.c_void_p]
+        h.rtwh_world_destroy.restype = None
+        h.rtwh_world_info.argtypes = [C.c_void_p, C.POINTER(Camera), C.c_int, C.POINTER(C.c_float)]
+        h.rtwh_world_flatten.argtypes = [C.c_void_p, C.POINTER(Sink), C.POINTER(BuildStats)]
         h.rtwh_open_image.argtypes = [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_void_p, C.c_size_t]
         h.rtwh_parse_obj.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
         h.rtwh_parse_obj.restype = C.c_longlong
@@ -293,6 +299,40 @@ def load_obj(path: str):
     return v, nr, uv
 
 
+class World:
+    """Scene::generate (scenes.rs:42-60) done once in the host front end: objects, cameras, background.  Flatten it
+    into as many backends as needed with Scene.from_world (generation is not repeated)."""
+
+    def __init__(self, name: str, aspect_ratio: float, seed: int = 1):
+        h = host_lib()
+        self.h = h.rtwh_world_create(name.encode(), aspect_ratio, seed)
+        if not self.h:
+            raise RtwError(f"world_create({name!r}): {h.rtwh_capi_error().decode()}")
+        cams = (Camera * 64)()
+        bg = (C.c_float * 3)()
+        n = h.rtwh_world_info(self.h, cams, 64, bg)
+        self.name = name
+        self.cameras = [Camera.from_buffer_copy(cams[i]) for i in range(min(n, 64))]
+        self.background = (bg[0], bg[1], bg[2])
+
+    def close(self):
+        if self.h:
+            host_lib().rtwh_world_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Scene:
     """A scene handle of one backend (rtw_scene* for the CUDA library)."""
 
@@ -348,6 +388,24 @@ class Scene:
             raise RtwError(f"build_scene({name!r}): {msg}")
         s.cameras = [Camera.from_buffer_copy(cams[i]) for i in range(min(n, 64))]
         s.background = (bg[0], bg[1], bg[2])
+        s.build_stats = st
+        return s
+
+    @classmethod
+    def from_world(cls, backend: Backend, world: "World", device: int = 0) -> "Scene":
+        """Flatten an already generated World into `backend` and build it (the second half of from_name)."""
+        h = host_lib()
+        sink = Sink()
+        if h.rtwh_sink_open(backend.path.encode(), backend.prefix.encode(), device, C.byref(sink)) < 0:
+            raise RtwError(h.rtwh_last_error().decode())
+        s = cls(backend, device, _sink=sink)
+        st = BuildStats()
+        if h.rtwh_world_flatten(world.h, C.byref(sink), C.byref(st)) < 0:
+            msg = h.rtwh_capi_error().decode()
+            s.close()
+            raise RtwError(f"world_flatten({world.name!r}): {msg}")
+        s.cameras = list(world.cameras)
+        s.background = world.background
         s.build_stats = st
         return s
 

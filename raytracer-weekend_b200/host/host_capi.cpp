@@ -82,6 +82,39 @@ int rtwh_build_scene(const char* name, float aspect_ratio, uint64_t seed, rtw_si
   }
 }
 
+// The two halves of rtwh_build_scene, separately: generate a world once (Scene::generate), flatten it into any number
+// of sinks.  A world handle is a heap-allocated rtwh::World.
+void* rtwh_world_create(const char* name, float aspect_ratio, uint64_t seed) {
+  if (!name) { fail(RTW_ERR_INVALID, "world_create: name is NULL"); return nullptr; }
+  try {
+    return new rtwh::World(rtwh::generate_scene(name, aspect_ratio, seed));
+  } catch (const std::exception& e) {
+    fail(RTW_ERR_INVALID, e.what());
+    return nullptr;
+  }
+}
+void rtwh_world_destroy(void* world) { delete (rtwh::World*)world; }
+// cameras: up to max_cams are written; returns the number of cameras of the world
+int rtwh_world_info(const void* world, rtw_camera* cams, int max_cams, float background[3]) {
+  if (!world) return fail(RTW_ERR_INVALID, "world_info: world is NULL");
+  const rtwh::World& w = *(const rtwh::World*)world;
+  for (int i = 0; cams && i < (int)w.cameras.size() && i < max_cams; ++i) cams[i] = w.cameras[i].c;
+  if (background) {
+    background[0] = w.background.x(); background[1] = w.background.y(); background[2] = w.background.z();
+  }
+  return (int)w.cameras.size();
+}
+// flatten (emit calls in canonical order) + rtw_build on the sink's backend
+int rtwh_world_flatten(const void* world, rtw_sink* sink, rtw_build_stats* stats) {
+  if (!world || !sink) return fail(RTW_ERR_INVALID, "world_flatten: NULL argument");
+  try {
+    rtwh::flatten_world(((const rtwh::World*)world)->objects, sink, 0.0f, 1.0f, stats);
+    return RTW_OK;
+  } catch (const std::exception& e) {
+    return fail(RTW_ERR_INVALID, e.what());
+  }
+}
+
 // Camera::new (camera.rs:25-64)
 int rtwh_camera_new(const float look_from[3], const float look_at[3], const float up[3], float vfov, float aspect,
                     float aperture, float focus_dist, float time0, float time1, rtw_camera* out) {

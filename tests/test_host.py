@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import raytracer_weekend_b200 as rtw
-from conftest import ROOT
+from conftest import ROOT, bits
 
 REF_MODELS = "/root/reference/models"
 
@@ -414,3 +414,20 @@ def test_progress_stream_through_the_receiver_stand_in():
     top_down = (np.float32(255.999) * c).astype(np.uint8)        # the frame as console_app writes it (main.rs:66-90)
     # receiver: y = Pixel.row = h-1-y_top, then rotate180 -> y_top, x mirrored
     assert np.array_equal(frames[0], top_down[:, ::-1])
+
+
+def test_world_generated_once_flattens_like_from_name(oracle):
+    """rtwh_world_create + rtwh_world_flatten = the two halves of rtwh_build_scene: same canonical ids, same cameras,
+    same closest hits, and one World can feed several scenes."""
+    with rtw.World("jumpy-balls", 16 / 9, seed=4) as world:
+        assert len(world.cameras) == 1 and world.background == pytest.approx((0.7, 0.8, 1.0))
+        with rtw.Scene.from_world(oracle, world) as a, rtw.Scene.from_world(oracle, world) as b, \
+                rtw.Scene.from_name(oracle, "jumpy-balls", 16 / 9, seed=4) as c:
+            assert a.num_prims == b.num_prims == c.num_prims
+            assert bytes(a.cameras[0]) == bytes(c.cameras[0])
+            rays = oracle.capture_rays(c, c.cameras[0], 64, 36, 3, 0, 0)
+            ha, hb, hc = a.trace_closest(rays), b.trace_closest(rays), c.trace_closest(rays)
+            assert np.array_equal(ha["prim_id"], hc["prim_id"]) and np.array_equal(hb["t"], hc["t"])
+            assert np.array_equal(ha["material_id"], hc["material_id"]) and np.array_equal(bits(ha["normal"]), bits(hc["normal"]))
+    with pytest.raises(rtw.RtwError, match="unknown scene"):
+        rtw.World("nope", 1.0)
