@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RTW_ABI_VERSION 1
+#define RTW_ABI_VERSION 2 /* 2: rtw_render_params.gpus, rtw_render_stats.fused / gpus, rtw_scene_clone */
 
 /* error codes */
 #define RTW_OK 0
@@ -93,6 +93,11 @@ typedef struct rtw_render_params {
   uint32_t pool_size;     /* path slots in flight; 0 -> auto                              */
   uint32_t slices;        /* sample slices per pixel (summation tree); 0 -> auto          */
   uint32_t flags;         /* RTW_RENDER_*                                                 */
+  uint32_t gpus;          /* rtw_render / rtw_render_frames: spread the frame over this many */
+                          /*   devices of the box (scene's device first, then the following  */
+                          /*   ones; replicas are made on first use); 0 or 1 -> one device.  */
+                          /*   The frame has the same bits for every value.                  */
+  uint32_t reserved;      /* 0                                                             */
 } rtw_render_params;
 
 #define RTW_RENDER_COUNT_TRAVERSAL 1u /* also count BVH node visits / primitive tests (slower) */
@@ -114,6 +119,9 @@ typedef struct rtw_render_stats {
   float ms_shade;         /* summed CUDA-event time of the shade kernel (if timed)         */
   float node_record_bytes;/* bytes one node_visit fetches: 64 (fp32 pair) or 32 (compact    */
                           /*   pair, hierarchies beyond the caches); 0 = not applicable      */
+  uint32_t fused;         /* 1: one-leaf scene rendered by the fused persistent kernel (no   */
+                          /*   wavefront, one launch per frame)                              */
+  uint32_t gpus;          /* devices that rendered this frame                               */
 } rtw_render_stats;
 
 typedef struct rtw_build_stats {
@@ -143,6 +151,12 @@ const char *rtw_last_error(void);
 int rtw_device_count(void);              /* number of CUDA devices, < 0 on error             */
 int rtw_scene_create(int device, rtw_scene **out);
 int rtw_scene_destroy(rtw_scene *s);
+/* A replica of a BUILT scene on another device: every device buffer (geometry, LBVH, materials, textures) is copied
+ * device to device (NVLink when the devices are peers) — the scene is neither re-flattened nor rebuilt, so all
+ * replicas hold bit-identical data.  SURVEY.md 8(e): "build on GPU 0 and broadcast the node / primitive arrays". */
+int rtw_scene_clone(const rtw_scene *src, int device, rtw_scene **out);
+/* events / streams / graphs this library holds right now (0 once every scene is destroyed): leak check for tests */
+int rtw_debug_live_handles(void);
 
 /* ---- textures: texture.rs, image_texture.rs ---------------------------------------------- */
 int rtw_add_texture_solid(rtw_scene *s, float r, float g, float b);            /* texture.rs:45-60  */
@@ -231,7 +245,12 @@ int rtw_trace_closest_device(rtw_scene *s, const rtw_ray *d_rays, uint64_t n, rt
 /* accum_rgb: width*height*3 floats, pixel (row, column) at ((height-1-row)*width + column)*3,
  * i.e. the order in which the reference yields its Pixels (row = bottom-up like Pixel.row,
  * lib.rs:58,120-126).  Value = un-normalised SUM over the rendered samples (lib.rs:82-94).
- * Pixels outside this call's tile partition are written as 0. */
+ * Pixels outside this call's tile partition are written as 0.
+ * params->gpus > 1 (the `gpus` argument of SURVEY.md 8b): one process drives that many devices — the scene is
+ * replicated with rtw_scene_clone on first use, device i renders the 32x32 tiles k with k % gpus == i (one host
+ * thread per device) and stores its finished pixels straight into the frame on the scene's device through peer
+ * memory (NVLink / NVSwitch; a staged peer copy when the devices are not peers), then ONE device-to-host copy.
+ * part_rank / part_count must be 0 in that case. */
 int rtw_render(rtw_scene *s, const rtw_camera *cam, const rtw_render_params *params,
                float *accum_rgb, rtw_render_stats *stats /* may be NULL */);
 /* device-resident variant: d_accum_rgb is device memory of the scene's device; work is queued on

@@ -51,14 +51,16 @@ class RenderParams(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("spp", C.c_uint32), ("max_depth", C.c_uint32),
                 ("background", C.c_float * 3), ("sample_begin", C.c_uint32), ("sample_end", C.c_uint32),
                 ("seed", C.c_uint64), ("tile_size", C.c_uint32), ("part_rank", C.c_uint32), ("part_count", C.c_uint32),
-                ("pool_size", C.c_uint32), ("slices", C.c_uint32), ("flags", C.c_uint32)]
+                ("pool_size", C.c_uint32), ("slices", C.c_uint32), ("flags", C.c_uint32), ("gpus", C.c_uint32),
+                ("reserved", C.c_uint32)]
 
 
 class RenderStats(C.Structure):
     _fields_ = [("segments", C.c_uint64), ("paths", C.c_uint64), ("node_visits", C.c_uint64), ("prim_tests", C.c_uint64),
                 ("prim_bytes", C.c_uint64),
                 ("iterations", C.c_uint32), ("launches", C.c_uint32), ("pool_size", C.c_uint32), ("slices", C.c_uint32),
-                ("ms_render", C.c_float), ("ms_traverse", C.c_float), ("ms_shade", C.c_float), ("node_record_bytes", C.c_float)]
+                ("ms_render", C.c_float), ("ms_traverse", C.c_float), ("ms_shade", C.c_float), ("node_record_bytes", C.c_float),
+                ("fused", C.c_uint32), ("gpus", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -157,6 +159,8 @@ class Backend:
             f("scene_num_instances").argtypes = [C.c_void_p]
             f("scene_prim_info").argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
             f("scene_instance_ops").argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        if self.has("scene_clone"):
+            f("scene_clone").argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
 
     def last_error(self) -> str:
         return (self.fn("last_error")() or b"").decode(errors="replace")
@@ -168,6 +172,10 @@ class Backend:
 
     def device_count(self) -> int:
         return int(self.fn("device_count")())
+
+    def live_handles(self) -> int:
+        """rtw_debug_live_handles: CUDA events / streams / graphs the library holds right now."""
+        return int(self.fn("debug_live_handles")())
 
     def new_scene(self, device: int = 0) -> "Scene":
         return Scene(self, device)
@@ -409,6 +417,15 @@ class Scene:
         s.build_stats = st
         return s
 
+    def clone(self, device: int) -> "Scene":
+        """rtw_scene_clone: a replica of this built scene on another device (buffers copied device to device)."""
+        h = C.c_void_p()
+        self.b.check(self.b.fn("scene_clone")(self.h, device, C.byref(h)), "scene_clone")
+        s = Scene.__new__(Scene)
+        s.b, s._sink, s.h = self.b, None, h
+        s.cameras, s.background, s.build_stats = list(self.cameras), self.background, self.build_stats
+        return s
+
     # -- emit calls (mirror of rtw_cuda.h) ------------------------------------------------------------
     def _c(self, name, *args):
         return self.b.check(self.b.fn(name)(self.h, *args), name)
@@ -492,11 +509,11 @@ class Scene:
         return hits
 
     def params(self, width, height, spp, *, max_depth=50, background=None, seed=0, sample_begin=0, sample_end=0,
-               tile_size=0, part_rank=0, part_count=0, pool_size=0, slices=0, flags=0) -> RenderParams:
+               tile_size=0, part_rank=0, part_count=0, pool_size=0, slices=0, flags=0, gpus=0) -> RenderParams:
         bg = self.background if background is None else background
         p = RenderParams(width=width, height=height, spp=spp, max_depth=max_depth, sample_begin=sample_begin,
                          sample_end=sample_end, seed=seed, tile_size=tile_size, part_rank=part_rank,
-                         part_count=part_count, pool_size=pool_size, slices=slices, flags=flags)
+                         part_count=part_count, pool_size=pool_size, slices=slices, flags=flags, gpus=gpus)
         p.background[0], p.background[1], p.background[2] = bg
         return p
 
@@ -511,6 +528,15 @@ class Scene:
         """rtw_render_device: d_accum_ptr = device pointer to width*height*3 floats."""
         st = RenderStats()
         self._c("render_device", C.byref(cam), C.byref(params), C.c_void_p(d_accum_ptr), C.c_void_p(stream), C.byref(st))
+        return st
+
+    def render_device_stats(self, cam: Camera, params: RenderParams) -> RenderStats:
+        """rtw_render_device into a scratch frame allocated for the call (host gets only the stats)."""
+        import torch
+
+        buf = torch.empty(params.width * params.height * 3, dtype=torch.float32, device=torch.device("cuda", 0))
+        st = self.render_device(cam, params, buf.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
         return st
 
     def render_frames(self, cams, params: RenderParams, on_frame=None) -> int:

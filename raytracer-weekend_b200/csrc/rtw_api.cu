@@ -103,13 +103,27 @@ int rtw_scene_create(int device, rtw_scene** out) {
 int rtw_scene_destroy(rtw_scene* s) {
   if (!s) return RTW_OK;
   if (s->built || s->wave) {
+    free_replicas(s);
     cudaSetDevice(s->device);
     free_wave(s);
     free_scene_device(s);
+    if (s->io_frame) cudaFree(s->io_frame);
+    if (s->io_pinned) cudaFreeHost(s->io_pinned);
   }
   delete s;
   return RTW_OK;
 }
+
+int rtw_scene_clone(const rtw_scene* src, int device, rtw_scene** out) {
+  if (!src || !out) return set_error(RTW_ERR_INVALID, "clone: NULL argument");
+  if (!src->built) return set_error(RTW_ERR_STATE, "scene not built (call rtw_build)");
+  int rc = clone_scene(src, device, out);
+  if (rc == RTW_OK) (*out)->is_replica = false;  // a caller-owned scene like any other
+  cudaSetDevice(src->device);
+  return rc;
+}
+
+int rtw_debug_live_handles(void) { return live_handles(); }
 
 // ---- textures ----------------------------------------------------------------------------------
 int rtw_add_texture_solid(rtw_scene* s, float r, float g, float b) {
@@ -523,7 +537,30 @@ int rtw_render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_para
                       void* stream, rtw_render_stats* stats) {
   CHECK_BUILT(s);
   if (!cam || !params || !d_accum_rgb) return set_error(RTW_ERR_INVALID, "render: NULL argument");
-  return render_device(s, cam, params, d_accum_rgb, (cudaStream_t)stream, stats);
+  if (params->gpus > 1) return set_error(RTW_ERR_INVALID, "render_device: gpus > 1 is a feature of rtw_render / rtw_render_frames");
+  int rc = render_device(s, cam, params, d_accum_rgb, (cudaStream_t)stream, stats);
+  if (rc == RTW_OK && stats) stats->gpus = 1;
+  return rc;
+}
+
+// the frame buffer on the scene's device and its pinned host staging: kept on the scene, grow only
+static int ensure_io(rtw_scene* s, size_t bytes) {
+  if (s->io_bytes >= bytes) return RTW_OK;
+  if (s->io_frame) cudaFree(s->io_frame);
+  if (s->io_pinned) cudaFreeHost(s->io_pinned);
+  s->io_frame = nullptr;
+  s->io_pinned = nullptr;
+  s->io_bytes = 0;
+  cudaError_t e = cudaMalloc((void**)&s->io_frame, bytes);
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&s->io_pinned, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    if (s->io_frame) cudaFree(s->io_frame);
+    s->io_frame = nullptr;
+    return set_error(RTW_ERR_NOMEM, std::string("render: frame buffer allocation failed: ") + cudaGetErrorString(e));
+  }
+  s->io_bytes = bytes;
+  return RTW_OK;
 }
 
 int rtw_render(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* params, float* accum_rgb,
@@ -531,20 +568,18 @@ int rtw_render(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* par
   CHECK_BUILT(s);
   if (!cam || !params || !accum_rgb) return set_error(RTW_ERR_INVALID, "render: NULL argument");
   RTW_CUDA_TRY(cudaSetDevice(s->device));
-  size_t bytes = (size_t)params->width * params->height * 3 * sizeof(float);
-  float* d_accum = nullptr;
-  cudaError_t e = cudaMalloc((void**)&d_accum, bytes ? bytes : 4);
-  if (e != cudaSuccess) {
-    cudaGetLastError();
-    return set_error(RTW_ERR_NOMEM, "render: cudaMalloc failed");
-  }
-  int rc = render_device(s, cam, params, d_accum, 0, stats);
-  if (rc == RTW_OK) {
-    e = cudaMemcpy(accum_rgb, d_accum, bytes, cudaMemcpyDeviceToHost);
-    if (e != cudaSuccess) rc = cuda_fail(e, "rtw_render readback");
-  }
-  cudaFree(d_accum);
-  return rc;
+  const size_t bytes = (size_t)params->width * params->height * 3 * sizeof(float);
+  int rc = ensure_io(s, std::max<size_t>(bytes, 4));
+  if (rc != RTW_OK) return rc;
+  rc = params->gpus > 1 ? render_multi_device(s, cam, params, s->io_frame, stats)
+                        : render_device(s, cam, params, s->io_frame, 0, stats);
+  if (rc != RTW_OK) return rc;
+  if (stats && stats->gpus == 0) stats->gpus = 1;
+  // device -> pinned staging at link speed, then into the caller's (pageable) buffer
+  cudaError_t e = cudaMemcpy(s->io_pinned, s->io_frame, bytes, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return cuda_fail(e, "rtw_render readback");
+  memcpy(accum_rgb, s->io_pinned, bytes);
+  return RTW_OK;
 }
 
 // scenes.rs:622-667 + main.rs:48-95: every camera over one resident world; D2H of frame i and its callback
@@ -595,7 +630,9 @@ int rtw_render_frames(rtw_scene* s, const rtw_camera* cameras, uint32_t n_frames
     }
     rtw_render_params p = *params;
     p.seed = params->seed + f;
-    rc = render_device(s, &cameras[f], &p, d_accum[b], 0, &stats[b]);  // returns when the frame is complete on the device
+    rc = p.gpus > 1 ? render_multi_device(s, &cameras[f], &p, d_accum[b], &stats[b])
+                    : render_device(s, &cameras[f], &p, d_accum[b], 0, &stats[b]);  // returns when the frame is complete on the device
+    if (rc == RTW_OK && stats[b].gpus == 0) stats[b].gpus = 1;
     if (rc != RTW_OK) break;
     if (!on_frame) {
       delivered++;

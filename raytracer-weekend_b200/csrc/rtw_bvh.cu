@@ -587,6 +587,7 @@ int dev_alloc(rtw_scene* s, T** out, size_t count) {
     return set_error(RTW_ERR_NOMEM, std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
   }
   s->allocations.push_back(p);
+  s->allocation_bytes.push_back(bytes);
   s->device_bytes += bytes;
   *out = (T*)p;
   return RTW_OK;
@@ -606,6 +607,7 @@ int dev_upload(rtw_scene* s, P* out, const std::vector<T>& v) {
 void free_scene_device(rtw_scene* s) {
   for (void* p : s->allocations) cudaFree(p);
   s->allocations.clear();
+  s->allocation_bytes.clear();
   s->device_bytes = 0;
 }
 
@@ -643,6 +645,8 @@ int build_scene_device(rtw_scene* s, float time0, float time1, rtw_build_stats* 
   d.num_prims = n;
   d.num_nodes = n > 1 ? n - 1 : 1;
   d.has_instances = s->inst_range.size() > 1 ? 1u : 0u;
+  d.num_insts = (uint32_t)s->inst_range.size();
+  d.num_inst_ops = (uint32_t)s->inst_ops.size();
   d.has_tri_shade = s->tri_shade.empty() ? 0u : 1u;
   d.has_media = 0;
   for (uint32_t m : s->prim_meta)
@@ -736,11 +740,14 @@ int build_scene_device(rtw_scene* s, float time0, float time1, rtw_build_stats* 
                     d_nodes, d_root, d_info);
   if (n > 1) k_sort_leaf_ranges<<<G, T>>>(n - 1, d_collapsed, d_nparent, d_nrange, d.prim_meta, d_v0);
   k_emit_leaves<<<G, T>>>(n, d_v0, d_enc, d.prim_meta, d.prim_mat, d.prim_shade, d_geom, d_slot_prim, d_slot_meta, d_slot_ms);
-  {
-    float4* d_nodes4;
-    if ((rc = dev_alloc(s, &d_nodes4, 8 * (size_t)d.num_nodes))) return rc;
-    k_build_wide<<<(d.num_nodes + T - 1) / T, T>>>(d.num_nodes, d_nodes, d_nodes4);
-    d.nodes4 = d_nodes4;
+  d.nodes4 = nullptr;
+  if (const char* e = getenv("RTW_WIDE")) {  // the 4-wide records exist only for the experiment that reads them
+    if (atoi(e) != 0) {
+      float4* d_nodes4;
+      if ((rc = dev_alloc(s, &d_nodes4, 8 * (size_t)d.num_nodes))) return rc;
+      k_build_wide<<<(d.num_nodes + T - 1) / T, T>>>(d.num_nodes, d_nodes, d_nodes4);
+      d.nodes4 = d_nodes4;
+    }
   }
   d.top_nodes = nullptr;
   d.top_count = 0;

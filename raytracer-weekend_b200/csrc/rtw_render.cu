@@ -1,23 +1,34 @@
-// Wavefront path tracer: the GPU form of Raytracer::render (lib.rs:57-117).
+// The GPU form of Raytracer::render (lib.rs:57-117).  Two schedules over the same arithmetic:
 //
-//   pool of P path slots (SoA in HBM) ──► k_wave_traverse ──► k_wave_shade ──► next queue
+//  (1) scenes with a hierarchy — WAVEFRONT:
+//        pool of P path slots (SoA in HBM) ──► k_wave_traverse ──► k_wave_shade ──► next iteration
+//  (2) one-leaf scenes (<= 32 primitives, e.g. the Cornell box) — FUSED persistent kernel k_mega_flat: there is no
+//      tree to walk, every ray tests the same primitive list, so nothing is gained by splitting intersection from
+//      shading; a lane keeps its path in registers from the camera to its end and the scene sits in shared memory.
+//      No path state ever touches HBM; a frame is ONE launch.
 //
-// * A slot owns one WORK ITEM = (pixel, sample slice): it runs the samples of that slice one after
-//   the other (lib.rs:83-88), adding each path's radiance to a running sum in sample order, writes
-//   the slice sum when done and pulls the next item from a global cursor (path regeneration), so
-//   the pool stays full until the frame runs dry.  Slices of a pixel are added in slice order by
-//   k_wave_resolve.  Every float addition therefore happens in an order fixed by (spp, slices)
-//   alone — the image is bit-reproducible for any pool size, GPU count or scheduling.
-// * sample_ray's recursion (lib.rs:97-117) is run in its iterative form L += T*e; T *= a
-//   (SURVEY.md §8 a3); one iteration of the wavefront = one path segment per live slot.
-// * Both kernels are persistent: grid = SMs x resident blocks, warps pull 32 entries at a time from
-//   a device-side cursor, so no launch parameter depends on the live count and the host only
-//   synchronises every few iterations to learn whether anything is left.
-// * While work items remain every slot is busy, so entry i of an iteration simply IS slot i
-//   ("identity" mode: coalesced state accesses, no queue, no compaction atomics).  Once the item
-//   cursor has run dry the shade kernel compacts the surviving slots into a queue each iteration
-//   ("queue" mode), so the tail of the frame costs time proportional to the live paths.
+// Common to both:
+// * A WORK ITEM = (pixel, sample slice).  Whoever owns the item (a pool slot / a lane) runs the samples of that slice
+//   one after the other (lib.rs:83-88), adding each path's radiance to a running sum in sample order, writes the slice
+//   sum when done and pulls the next item from a global cursor (path regeneration).  Slices of a pixel are added in
+//   slice order by k_wave_resolve.  Every float addition therefore happens in an order fixed by (spp, slices) alone —
+//   the image is bit-reproducible for any pool size, GPU count, schedule (1) or (2), or scheduling.
+// * The default slice count depends on (width, height, samples, scene class) only — never on the pool or on the tile
+//   partition — so a frame rendered by 8 GPUs has the same bits as the frame rendered by one.
+// * sample_ray's recursion (lib.rs:97-117) is run in its iterative form L += T*e; T *= a.
+//
+// Wavefront specifics:
+// * Both kernels are persistent: grid = SMs x resident blocks, warps pull 32 entries at a time from a device-side
+//   cursor, so no launch parameter depends on the live count and the host only looks at the live count every BATCH
+//   iterations, one round late.
+// * While work items remain every slot is busy, so entry i of an iteration simply IS slot i ("identity" mode:
+//   coalesced state accesses, no queue, no compaction atomics).  Once the item cursor has run dry the shade kernel
+//   compacts the surviving slots into a queue each iteration ("queue" mode).
+// * The per-frame values (camera, seed, frame pointer ...) live in a FrameDev record in device memory, so the
+//   instantiated CUDA graph of BATCH iterations, the events and the pool are created once per scene and reused by
+//   every later frame (r01 re-captured and re-instantiated the graph and created ~10 events per frame).
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -27,20 +38,44 @@
 
 namespace rtw {
 
+// ---- handle accounting (tests/test_gpu_parity.py::test_failed_render_leaks_nothing) ----------------------------------
+static std::atomic<int> g_live_handles{0};
+int live_handles() { return g_live_handles.load(); }
+void count_handle(int delta) { g_live_handles += delta; }
+
 namespace {
 
-#define RTW_MAX_SUBPOOLS 4
-#ifndef RTW_SHADE_STATIC
-#define RTW_SHADE_STATIC 0  // static trips + L2 prefetch of the next trip: Cornell shade -5 %, cow +7 % (imbalance): off
-#endif
-#ifndef RTW_WIDE_HIT
-#define RTW_WIDE_HIT 0  // A/B r01: 16-byte hit record (meta + material): shade +-0, traversal +1-2 % slower
-#endif
+cudaError_t new_event(cudaEvent_t* e, unsigned flags) {
+  cudaError_t r = cudaEventCreateWithFlags(e, flags);
+  if (r == cudaSuccess) count_handle(1);
+  return r;
+}
+void drop_event(cudaEvent_t& e) {
+  if (e) { cudaEventDestroy(e); count_handle(-1); e = nullptr; }
+}
+cudaError_t new_stream(cudaStream_t* s) {
+  cudaError_t r = cudaStreamCreateWithFlags(s, cudaStreamNonBlocking);
+  if (r == cudaSuccess) count_handle(1);
+  return r;
+}
+void drop_stream(cudaStream_t& s) {
+  if (s) { cudaStreamDestroy(s); count_handle(-1); s = nullptr; }
+}
+struct EventBag {  // events of one call (per-kernel timing): destroyed on every way out
+  std::vector<cudaEvent_t> v;
+  ~EventBag() { for (auto& e : v) drop_event(e); }
+  cudaError_t add(cudaEvent_t* out) {
+    cudaError_t r = new_event(out, cudaEventDefault);
+    if (r == cudaSuccess) v.push_back(*out);
+    return r;
+  }
+};
+
 // ray_d.w of a slot: 0 = a live ray, else
 #define RTW_SLOT_DEAD 1.0f     // no work left for the slot (end of the frame, identity mode)
-#define RTW_SLOT_PENDING 2.0f  // traversal suspended in the drain of the last launch (rtw_traverse.cuh)
+#define RTW_SLOT_PENDING 2.0f  // traversal suspended in the drain of the last launch (rtw_traverse.cuh; off by default)
 
-struct WaveCtl {           // one per sub-pool (+ one extra whose item_cursor is the shared work-item cursor)
+struct WaveCtl {
   unsigned long long item_cursor;
   unsigned long long segments;
   unsigned long long paths;
@@ -50,29 +85,22 @@ struct WaveCtl {           // one per sub-pool (+ one extra whose item_cursor is
   uint32_t count[2];       // entries of the iteration with that parity (identity mode: slot_count)
   uint32_t cursor_traverse;
   uint32_t cursor_shade;
-  uint32_t qmode[2];       // 0 = identity (entry i is slot slot_base + i), 1 = queue[parity] lists the live slots
-  uint32_t exhausted;      // (shared ctl only) the item cursor ran past n_items
+  uint32_t qmode[2];       // 0 = identity (entry i is slot i), 1 = queue[parity] lists the live slots
+  uint32_t exhausted;      // the item cursor ran past n_items
   uint32_t pad[3];
 };
 
 struct WaveDev {
   float4* ray_o;    // origin.xyz, time
-  float4* ray_d;    // direction.xyz, -
-#if RTW_WIDE_HIT
-  int4* hit;        // primitive slot (or -1), t bits, slot meta (type | inst << 3), material: what the shade kernel
-                    // would otherwise fetch through the slot in a dependent load
-#else
+  float4* ray_d;    // direction.xyz, slot flag
   int2* hit;        // primitive slot (or -1), t bits
-#endif
   float4* thr;      // throughput T.rgb
   float4* sum;      // running slice sum rgb
   uint4* state;     // pixel index (row*w+col), sample, sample_end, bounce | slice << 8
   uint32_t* queue[2];
   float4* partial;  // [slices][pix_per_slice] slice sums of the pixels this partition owns (slices > 1)
-  WaveCtl* ctl;                      // this sub-pool's counters
-  unsigned long long* item_cursor;   // shared by all sub-pools
-  uint32_t* exhausted;               // shared by all sub-pools
-  uint32_t slot_base, slot_count;    // this sub-pool's slots: [slot_base, slot_base + slot_count)
+  WaveCtl* ctl;
+  uint32_t slot_count;
 };
 
 struct FrameDev {
@@ -85,24 +113,41 @@ struct FrameDev {
   uint32_t seed_lo, seed_hi;
   unsigned long long pix_per_slice;  // owned tiles * tile_size^2 (includes out-of-image padding)
   unsigned long long n_items;
-  uint32_t pool;
-  uint32_t fit32;       // n_items, nsamp * slices < 2^32: decode_item stays in 32-bit arithmetic
-  uint32_t tile_shift;  // log2(tile_size) when it is a power of two, else 0xffffffff
+  uint32_t fit32;         // n_items, nsamp * slices < 2^32: decode_item stays in 32-bit arithmetic
+  uint32_t tile_shift;    // log2(tile_size) when it is a power of two, else 0xffffffff
+  uint32_t skip_unowned;  // k_wave_resolve leaves the pixels of other partitions untouched (multi-GPU: one shared frame)
+  uint32_t pad;
+  float* accum;           // the frame: width*height*3 sums (this device's memory, or a peer's over NVLink)
 };
 
-// the traversal kernel variants a render can launch
+// the traversal kernel variants a wavefront render can launch
 enum TravKind { TK_PAIR = 0, TK_MEDIA, TK_WIDE, TK_COMPACT, TK_COUNT, TK_COUNT_COMPACT, TK_FLAT, TK_N };
+
+struct GraphKey {
+  int kind = -1, batch = 0, grid_t = 0, grid_s = 0;
+  uint32_t pool = 0;
+  bool operator==(const GraphKey& o) const {
+    return kind == o.kind && batch == o.batch && grid_t == o.grid_t && grid_s == o.grid_s && pool == o.pool;
+  }
+};
 
 struct WaveHost {
   WaveDev dev{};
-  std::vector<void*> allocs;
-  uint32_t pool = 0;
+  std::vector<void*> pool_allocs;
+  uint32_t pool = 0;               // slots the pool arrays hold
+  float4* partial = nullptr;
   size_t partial_elems = 0;
-  WaveCtl* pinned_ctl = nullptr;   // [RTW_MAX_SUBPOOLS][2]: ring for the lagging termination check
-  cudaStream_t stream = nullptr;    // internal non-blocking stream (graph capture needs a non-legacy stream)
-  cudaStream_t pool_stream[RTW_MAX_SUBPOOLS] = {};
-  int blocks_trav[TK_N] = {};  // persistent grid per TravKind
+  WaveCtl* d_ctl = nullptr;
+  FrameDev* d_frame = nullptr;     // read by the wavefront kernels (they are baked into a cached graph)
+  FrameDev* h_frame = nullptr;     // pinned staging of d_frame
+  WaveCtl* pinned_ctl = nullptr;   // [2]: ring for the lagging termination check, [2] = final counters
+  cudaStream_t stream = nullptr;   // internal non-blocking stream (graph capture needs a non-legacy stream)
+  cudaEvent_t ev_in = nullptr, ev_begin = nullptr, ev_end = nullptr, ring_ev[2] = {nullptr, nullptr};
+  GraphKey graph_key;
+  cudaGraphExec_t graph_exec = nullptr;
+  int blocks_trav[TK_N] = {};      // persistent grid per TravKind
   int blocks_shade = 0;
+  int blocks_mega = 0;
 };
 
 // ---- work items ---------------------------------------------------------------------------------
@@ -167,18 +212,17 @@ __device__ __forceinline__ unsigned long long owned_index(const FrameDev& f, uin
 
 // Warp-cooperative fetch: every lane with `need` gets a valid item or learns that none are left.
 // Must be called by all 32 lanes.
-__device__ __forceinline__ bool fetch_item(const FrameDev& f, const WaveDev& w, bool need, Item& it) {
-  unsigned long long* item_cursor = w.item_cursor;
+__device__ __forceinline__ bool fetch_item(const FrameDev& f, WaveCtl* ctl, bool need, Item& it) {
   const uint32_t lane = threadIdx.x & 31;
   bool got = false;
   for (;;) {
     uint32_t m = __ballot_sync(0xffffffffu, need && !got);
     if (m == 0) break;
     unsigned long long base = 0;
-    if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(item_cursor, (unsigned long long)__popc(m));
+    if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(&ctl->item_cursor, (unsigned long long)__popc(m));
     base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
     if (base + __popc(m) > f.n_items) {  // ran dry (the cursor may overshoot; harmless): later iterations compact
-      if (lane == 0) *w.exhausted = 1u;
+      if (lane == 0) ctl->exhausted = 1u;
       if (base >= f.n_items) break;
     }
     if (need && !got) {
@@ -190,18 +234,73 @@ __device__ __forceinline__ bool fetch_item(const FrameDev& f, const WaveDev& w, 
   return got;
 }
 
-// lib.rs:84-86: start sample `it.sample` of the item's pixel.
-__device__ __forceinline__ void start_path(const FrameDev& f, const WaveDev& w, uint32_t slot, const Item& it) {
+// lib.rs:84-86: the camera ray of sample `it.sample` of the item's pixel (stage 0 of the path's stream).
+__device__ __forceinline__ void camera_path(const FrameDev& f, const Item& it, v3& o, v3& d, float& time) {
   Rng rng;
   rng.begin(((uint64_t)f.seed_hi << 32) | f.seed_lo, it.pixel, it.sample, 0);
   uint32_t row = it.pixel / f.width, col = it.pixel % f.width;
+  camera_ray(f.cam, f.width, f.height, row, col, rng, o, d, time);
+}
+
+__device__ __forceinline__ void start_path(const FrameDev& f, const WaveDev& w, uint32_t slot, const Item& it) {
   v3 o, d;
   float time;
-  camera_ray(f.cam, f.width, f.height, row, col, rng, o, d, time);
+  camera_path(f, it, o, d, time);
   w.ray_o[slot] = make_float4(o.x, o.y, o.z, time);
   w.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.f);
   w.thr[slot] = make_float4(1.f, 1.f, 1.f, 0.f);
   w.state[slot] = make_uint4(it.pixel, it.sample, it.sample_end, it.slice << 8);
+}
+
+// the slice sum of a finished work item: straight into the frame (one slice) or into the slice-sum buffer
+__device__ __forceinline__ void publish_item(const FrameDev& f, float4* __restrict__ partial, uint32_t pixel, uint32_t slice,
+                                             v3 sum) {
+  uint32_t row = pixel / f.width, col = pixel - row * f.width;
+  if (f.slices == 1) {
+    size_t pix = (size_t)(f.height - 1 - row) * f.width + col;
+    f.accum[3 * pix] = sum.x; f.accum[3 * pix + 1] = sum.y; f.accum[3 * pix + 2] = sum.z;
+  } else {
+    partial[(size_t)slice * f.pix_per_slice + owned_index(f, col, f.height - 1 - row)] = make_float4(sum.x, sum.y, sum.z, 0.f);
+  }
+}
+
+// One path segment after its closest-hit query (lib.rs:102-116): the ray (o, d, time) hit primitive type/inst with
+// geometry words g0..g2 at distance t.  Returns true when the path ENDS with this segment (L = the radiance it
+// contributes, throughput applied); otherwise T, bounce and the ray are advanced to the scattered ray.
+// Shared by the wavefront shade kernel and the fused flat-scene kernel: one copy of the parity-critical arithmetic.
+template <class IV>
+__device__ __forceinline__ bool shade_hit(const SceneDev& sc, const IV& iv, uint32_t max_depth, uint32_t meta,
+                                          const MaterialRec& m, int32_t shade_idx, float4 g0, float4 g1, float4 g2, float t,
+                                          uint64_t seed, uint32_t pixel, uint32_t sample, v3& o, v3& d, float time, v3& T,
+                                          uint32_t& bounce, v3& L) {
+  const bool need_uv = !m.solid && (m.type == MT_LAMBERTIAN || m.type == MT_DIFFUSE_LIGHT) && texture_needs_uv(sc, m.tex);
+  HitRec rec;
+  finalize_hit_iv(sc, iv, meta & 7u, meta >> RTW_META_TYPE_BITS, g0, g1, g2, shade_idx, o, d, time, t, need_uv, rec);
+  const v3 emitted = material_emitted(sc, m, rec);  // lib.rs:107-109
+  Rng rng;
+  rng.begin(seed, pixel, sample, bounce + 1);
+  v3 att, out_dir;
+  if (!material_scatter(sc, m, d, rec, rng, att, out_dir)) {  // lib.rs:111-114
+    L = T * emitted;
+    return true;
+  }
+  // L += T*emitted with emitted == 0 for every scattering material: exact no-op
+  T = T * att;  // lib.rs:116
+  bounce += 1;
+  if (bounce >= max_depth) {  // lib.rs:98-100: depth exhausted -> black
+    L = mk(0.f, 0.f, 0.f);
+    return true;
+  }
+  o = rec.p;
+  d = out_dir;
+  return false;
+}
+
+__device__ __forceinline__ void load_frame(FrameDev& fs, const FrameDev* __restrict__ fp) {
+  const uint32_t* __restrict__ src = reinterpret_cast<const uint32_t*>(fp);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(&fs);
+  for (uint32_t i = threadIdx.x; i < sizeof(FrameDev) / 4u; i += blockDim.x) dst[i] = src[i];
+  __syncthreads();
 }
 
 __device__ __forceinline__ void queue_push(uint32_t* queue, uint32_t* count, bool alive, uint32_t slot) {
@@ -214,15 +313,17 @@ __device__ __forceinline__ void queue_push(uint32_t* queue, uint32_t* count, boo
   if (alive) queue[base + __popc(m & ((1u << lane) - 1u))] = slot;
 }
 
-__global__ void k_wave_init(SceneDev sc, FrameDev f, WaveDev w) {
+__global__ void __launch_bounds__(128) k_wave_init(SceneDev sc, const FrameDev* __restrict__ fp, WaveDev w) {
+  __shared__ FrameDev f;
+  load_frame(f, fp);
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;  // block = 128 threads: whole warps reach the ballots
-  const uint32_t slot = w.slot_base + tid;
+  const uint32_t slot = tid;
   if (tid == 0) {  // iteration 0 reads the slots in identity mode
     w.ctl->count[0] = w.slot_count;
     w.ctl->qmode[0] = 0;
   }
   Item it;
-  bool got = fetch_item(f, w, tid < w.slot_count, it);
+  bool got = fetch_item(f, w.ctl, tid < w.slot_count, it);
   if (got) {
     start_path(f, w, slot, it);
     w.sum[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -238,46 +339,37 @@ struct WaveIO {
   const WaveDev& w;
   const uint32_t* __restrict__ queue;  // nullptr: identity mode
   uint32_t slot;
-  uint32_t seed_lo, seed_hi;
+  const FrameDev* __restrict__ fp;
   // key of the current path segment: (pixel, sample), stage = bounce + 1 — the stage the shade kernel uses
   __device__ __forceinline__ void rng_key(Rng& rng) {
     const uint4 st = w.state[slot];
-    rng.begin(((uint64_t)seed_hi << 32) | seed_lo, st.x, st.y, (st.w & 0xffu) + 1u);
+    rng.begin(((uint64_t)fp->seed_hi << 32) | fp->seed_lo, st.x, st.y, (st.w & 0xffu) + 1u);
   }
 #ifndef RTW_SUSPEND_LANES
 #define RTW_SUSPEND_LANES 0  // A/B r01 (cow, monument): 4 / 8 / 12 cost 3-12 % — the restarts outweigh the shorter drain
 #endif
   static constexpr int kSuspendLanes = RTW_SUSPEND_LANES;
   bool was_pending;
-  const int2* __restrict__ slot_ms;  // SceneDev::slot_ms
   __device__ __forceinline__ bool load(uint32_t i, v3& o, v3& d, float& time, float& t_min, float& t_max, int32_t& slot0,
                                        bool& resumed) {
-    slot = queue ? queue[i] : w.slot_base + i;
+    slot = queue ? queue[i] : i;
     const float4 o4 = w.ray_o[slot], d4 = w.ray_d[slot];
     if (d4.w == RTW_SLOT_DEAD) return false;  // identity mode at the end of the frame
     o = mk(o4.x, o4.y, o4.z); d = mk(d4.x, d4.y, d4.z); time = o4.w;
     t_min = 0.001f; t_max = __int_as_float(0x7f800000);  // lib.rs:102: world.hit(r, 0.001, f32::INFINITY)
     resumed = was_pending = d4.w == RTW_SLOT_PENDING;
     if (resumed) {  // suspended by the previous launch with this hit
-      const auto h = w.hit[slot];
+      const int2 h = w.hit[slot];
       slot0 = h.x; t_max = __int_as_float(h.y);
     }
     return true;
   }
-  __device__ __forceinline__ void store(uint32_t, v3, v3 d, float, int32_t hslot, float t, uint32_t meta) {
-#if RTW_WIDE_HIT
-    w.hit[slot] = make_int4(hslot, __float_as_int(t), (int)meta, hslot >= 0 ? slot_ms[hslot].x : 0);
-#else
+  __device__ __forceinline__ void store(uint32_t, v3, v3 d, float, int32_t hslot, float t, uint32_t) {
     w.hit[slot] = make_int2(hslot, __float_as_int(t));
-#endif
     if (was_pending) w.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.f);
   }
   __device__ __forceinline__ void suspend(uint32_t, int32_t hslot, float t) {
-#if RTW_WIDE_HIT
-    w.hit[slot] = make_int4(hslot, __float_as_int(t), 0, 0);
-#else
     w.hit[slot] = make_int2(hslot, __float_as_int(t));
-#endif
     const float4 d4 = w.ray_d[slot];
     w.ray_d[slot] = make_float4(d4.x, d4.y, d4.z, RTW_SLOT_PENDING);
   }
@@ -297,32 +389,32 @@ __device__ __forceinline__ void traverse_prologue(const WaveDev& w, uint32_t par
     ctl->cursor_shade = 0;  // consumed by the shade kernel that follows
     // What the shade kernel that follows writes for the next iteration: a queue once the work items have run
     // out (decided HERE, between launches, so that all of its blocks agree), else nothing (identity).
-    const uint32_t out_queue = (in_queue || *w.exhausted) ? 1u : 0u;
+    const uint32_t out_queue = (in_queue || ctl->exhausted) ? 1u : 0u;
     ctl->qmode[parity ^ 1] = out_queue;
     ctl->count[parity ^ 1] = out_queue ? 0u : w.slot_count;
   }
 }
 
-// Flat scenes (<= 32 primitives in one leaf): rtw_traverse.cuh, traverse_flat
-__global__ void __launch_bounds__(128, 8) k_wave_traverse_flat(SceneDev sc, WaveDev w, uint32_t parity, uint32_t seed_lo,
-                                                               uint32_t seed_hi) {
+// Flat scenes through the wavefront (instrumented runs, RTW_MEGA=0): rtw_traverse.cuh, traverse_flat
+__global__ void __launch_bounds__(128, 8) k_wave_traverse_flat(SceneDev sc, const FrameDev* __restrict__ fp, WaveDev w,
+                                                               uint32_t parity) {
   __shared__ FlatRecords fr;
   uint32_t count, in_queue;
   traverse_prologue(w, parity, count, in_queue);
   stage_flat(sc, fr);
-  WaveIO io{w, in_queue ? w.queue[parity] : nullptr, 0, seed_lo, seed_hi, false, sc.slot_ms};
+  WaveIO io{w, in_queue ? w.queue[parity] : nullptr, 0, fp, false};
   traverse_flat(sc, fr, io, count, &w.ctl->cursor_traverse);
 }
 
 template <bool COUNT, bool MEDIA, int NODES>
 __global__ void __launch_bounds__(128, (COUNT || MEDIA || NODES == NODES_WIDE) ? 1 : RTW_TRAVERSE_MINBLOCKS)
-    k_wave_traverse(SceneDev sc, WaveDev w, uint32_t parity, uint32_t seed_lo, uint32_t seed_hi) {
+    k_wave_traverse(SceneDev sc, const FrameDev* __restrict__ fp, WaveDev w, uint32_t parity) {
   WaveCtl* ctl = w.ctl;
   uint32_t count, in_queue;
   traverse_prologue(w, parity, count, in_queue);
   const uint32_t lane = threadIdx.x & 31;
   TraverseCounters cnt;
-  WaveIO io{w, in_queue ? w.queue[parity] : nullptr, 0, seed_lo, seed_hi, false, sc.slot_ms};
+  WaveIO io{w, in_queue ? w.queue[parity] : nullptr, 0, fp, false};
 #if RTW_TOP_TREE > 0
   __shared__ float4 top_smem[4 * RTW_TOP_TREE];
   stage_top_tree(sc, top_smem);
@@ -348,8 +440,8 @@ __global__ void __launch_bounds__(128, (COUNT || MEDIA || NODES == NODES_WIDE) ?
 // ---- shade + scatter + regenerate -----------------------------------------------------------------
 // A warp shades 32 queue entries per trip.  Paths that end in a trip (15 % of the lanes on Cornell) are NOT
 // restarted in place: that ran the whole regeneration code (work-item decode, Philox, camera ray) with 2.3 of
-// 32 lanes active — a quarter of the kernel's issued instructions (profiles/r01f_shade_lines.txt).  They go
-// on a per-warp backlog in shared memory instead; once 32 are waiting the warp restarts them together.
+// 32 lanes active.  They go on a per-warp backlog in shared memory instead; once 32 are waiting the warp restarts
+// them together.
 #define RTW_BACKLOG 64
 #define RTW_NEED_ITEM 0x80000000u
 
@@ -358,12 +450,7 @@ struct ShadeBacklog {  // per warp; SoA so that lane i touches bank i
 };
 
 // restart the paths of backlog entries [first, first + 32) (those with valid == true): lib.rs:83-86
-#ifdef RTW_NOINLINE_REGEN
-static __device__ __noinline__ void regenerate(
-#else
-__device__ __forceinline__ void regenerate(
-#endif
-const FrameDev& f, const WaveDev& w, ShadeBacklog& bl, uint32_t idx, bool valid,
+__device__ __forceinline__ void regenerate(const FrameDev& f, const WaveDev& w, ShadeBacklog& bl, uint32_t idx, bool valid,
                                            uint32_t* next_queue, uint32_t* next_count, bool out_queue,
                                            uint32_t& new_paths) {
   Item it;
@@ -376,7 +463,7 @@ const FrameDev& f, const WaveDev& w, ShadeBacklog& bl, uint32_t idx, bool valid,
     go = !need_item;
   }
   __syncwarp();
-  if (fetch_item(f, w, need_item, it)) {  // the slot finished its work item: pull the next one
+  if (fetch_item(f, w.ctl, need_item, it)) {  // the slot finished its work item: pull the next one
     w.sum[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
     go = true;
   }
@@ -389,14 +476,15 @@ const FrameDev& f, const WaveDev& w, ShadeBacklog& bl, uint32_t idx, bool valid,
   if (out_queue) queue_push(next_queue, next_count, go, slot);
 }
 
-#ifdef RTW_SHADE_MINBLOCKS  // A/B r01: 6 (80 registers) and 7 (72) are 4 % and 11 % slower than the default (94)
+#ifdef RTW_SHADE_MINBLOCKS  // A/B r01: 6 (80 registers) and 7 (72) are 4 % and 11 % slower than the compiler's choice
 __global__ void __launch_bounds__(128, RTW_SHADE_MINBLOCKS) k_wave_shade(
 #else
 __global__ void __launch_bounds__(128) k_wave_shade(
 #endif
-    SceneDev sc, FrameDev f, WaveDev w, float* __restrict__ accum,
-                                                    uint32_t parity) {
+    SceneDev sc, const FrameDev* __restrict__ fp, WaveDev w, uint32_t parity) {
   __shared__ ShadeBacklog backlog[4];
+  __shared__ FrameDev f;
+  load_frame(f, fp);
   ShadeBacklog& bl = backlog[threadIdx.x >> 5];
   WaveCtl* ctl = w.ctl;
   const uint32_t count = ctl->count[parity];
@@ -408,38 +496,15 @@ __global__ void __launch_bounds__(128) k_wave_shade(
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t lane_lt = (1u << lane) - 1u;
   const uint64_t seed = ((uint64_t)f.seed_hi << 32) | f.seed_lo;
+  const uint32_t max_depth = f.max_depth;
+  const GlobalInst iv{sc.inst_range, sc.inst_ops};
   uint32_t new_paths = 0, nseg = 0;
   uint32_t nback = 0;  // warp-uniform: entries waiting on the backlog
-#if RTW_SHADE_STATIC
-  // Identity mode: trips are handed out statically (warp w takes trips w, w + W, ...), so the NEXT trip's slots are
-  // known and their state can be started on its way into L2 while this trip is shaded.
-  const bool static_trips = queue == nullptr;
-  const uint32_t warps_total = gridDim.x * (blockDim.x >> 5);
-  uint32_t trip = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-#else
-  const bool static_trips = false;
-  uint32_t trip = 0;
-  const uint32_t warps_total = 0;
-#endif
   uint32_t grabbed = 0;
-  if (!static_trips && lane == 0) grabbed = atomicAdd(&ctl->cursor_shade, 32u);
+  if (lane == 0) grabbed = atomicAdd(&ctl->cursor_shade, 32u);
   for (;;) {
-    const uint32_t base = static_trips ? trip * 32u : __shfl_sync(0xffffffffu, grabbed, 0);
+    const uint32_t base = __shfl_sync(0xffffffffu, grabbed, 0);
     if (base >= count) break;
-#if RTW_SHADE_STATIC
-    if (static_trips) {
-      trip += warps_total;
-      const uint32_t nxt = trip * 32u + lane;
-      if (nxt < count) {
-        const uint32_t ns = w.slot_base + nxt;
-        prefetch_l2(&w.hit[ns]); prefetch_l2(&w.ray_o[ns]); prefetch_l2(&w.ray_d[ns]);
-        prefetch_l2(&w.thr[ns]); prefetch_l2(&w.state[ns]); prefetch_l2(&w.sum[ns]);
-      }
-    }
-#endif
-#ifdef RTW_CURSOR_PREFETCH
-    if (lane == 0) grabbed = atomicAdd(&ctl->cursor_shade, 32u);
-#endif
     const uint32_t i = base + lane;
     bool active = i < count;
     uint32_t slot = 0;
@@ -448,14 +513,10 @@ __global__ void __launch_bounds__(128) k_wave_shade(
     Item it;
     it.pixel = it.sample = it.sample_end = it.slice = 0;
     float4 o4, d4, T4, s4;
-#if RTW_WIDE_HIT
-    int4 h;
-#else
     int2 h;
-#endif
     uint4 st;
     if (active) {  // every load of the slot's state is issued before the first use
-      slot = queue ? queue[i] : w.slot_base + i;
+      slot = queue ? queue[i] : i;
       h = w.hit[slot];
       o4 = w.ray_o[slot]; d4 = w.ray_d[slot];
       T4 = w.thr[slot];
@@ -473,41 +534,23 @@ __global__ void __launch_bounds__(128) k_wave_shade(
         L = T * f.background;
         ended = true;
       } else {
-#if RTW_WIDE_HIT
-        const uint32_t meta = (uint32_t)h.z;
-        const MaterialRec m = sc.materials[h.w];
-        // only a triangle with per-vertex normals / uvs needs its TriShade index (one more hop through the slot)
-        int2 ms = make_int2(h.w, -1);
-        if ((meta & 7u) == PT_TRI && sc.has_tri_shade) ms.y = sc.slot_ms[h.x].y;
-#else
         const uint32_t meta = sc.slot_meta[h.x];
         const int2 ms = sc.slot_ms[h.x];
         const MaterialRec m = sc.materials[ms.x];
-#endif
-        const v3 o = mk(o4.x, o4.y, o4.z), d = mk(d4.x, d4.y, d4.z);
-        const bool need_uv = !m.solid && (m.type == MT_LAMBERTIAN || m.type == MT_DIFFUSE_LIGHT) && texture_needs_uv(sc, m.tex);
-        HitRec rec;
-        finalize_hit(sc, meta & 7u, meta >> RTW_META_TYPE_BITS, sc.geom + 3 * (size_t)h.x, ms.y, o, d, o4.w,
-                     __int_as_float(h.y), need_uv, rec);
-        const v3 emitted = material_emitted(sc, m, rec);  // lib.rs:107-109
-        Rng rng;
-        rng.begin(seed, st.x, st.y, bounce + 1);
-        v3 att, out_dir;
-        if (!material_scatter(sc, m, d, rec, rng, att, out_dir)) {  // lib.rs:111-114
-          L = T * emitted;
-          ended = true;
-        } else {
-          // L += T*emitted with emitted == 0 for every scattering material: exact no-op
-          T = T * att;  // lib.rs:116
-          bounce += 1;
-          ended = bounce >= f.max_depth;  // lib.rs:98-100: depth exhausted -> black
-          if (!ended) {
-            w.ray_o[slot] = make_float4(rec.p.x, rec.p.y, rec.p.z, o4.w);
-            w.ray_d[slot] = make_float4(out_dir.x, out_dir.y, out_dir.z, 0.f);
-            w.thr[slot] = make_float4(T.x, T.y, T.z, 0.f);
-            w.state[slot] = make_uint4(st.x, st.y, st.z, (st.w & ~0xffu) | bounce);
-            alive = true;
-          }
+        const uint32_t type = meta & 7u;
+        const float4* __restrict__ g = sc.geom + 3 * (size_t)h.x;
+        const float4 g0 = __ldg(g);
+        float4 g1 = make_float4(0.f, 0.f, 0.f, 0.f), g2 = g1;
+        if (type == PT_MSPHERE || type == PT_TRI) { g1 = __ldg(g + 1); g2 = __ldg(g + 2); }
+        v3 o = mk(o4.x, o4.y, o4.z), d = mk(d4.x, d4.y, d4.z);
+        ended = shade_hit(sc, iv, max_depth, meta, m, ms.y, g0, g1, g2, __int_as_float(h.y), seed, st.x, st.y, o, d, o4.w, T,
+                          bounce, L);
+        if (!ended) {
+          w.ray_o[slot] = make_float4(o.x, o.y, o.z, o4.w);
+          w.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.f);
+          w.thr[slot] = make_float4(T.x, T.y, T.z, 0.f);
+          w.state[slot] = make_uint4(st.x, st.y, st.z, (st.w & ~0xffu) | bounce);
+          alive = true;
         }
       }
       if (ended) {
@@ -516,14 +559,7 @@ __global__ void __launch_bounds__(128) k_wave_shade(
         if (st.y + 1 < st.z) {  // next sample of the same item
           w.sum[slot] = make_float4(sum.x, sum.y, sum.z, 0.f);
         } else {  // item done: publish the slice sum
-          uint32_t row = st.x / f.width, col = st.x - row * f.width;
-          size_t pix = (size_t)(f.height - 1 - row) * f.width + col;
-          if (f.slices == 1) {
-            accum[3 * pix] = sum.x; accum[3 * pix + 1] = sum.y; accum[3 * pix + 2] = sum.z;
-          } else {
-            w.partial[(size_t)(st.w >> 8) * f.pix_per_slice + owned_index(f, col, f.height - 1 - row)] =
-                make_float4(sum.x, sum.y, sum.z, 0.f);
-          }
+          publish_item(f, w.partial, st.x, st.w >> 8, sum);
           it.slice = RTW_NEED_ITEM;
         }
       }
@@ -537,16 +573,10 @@ __global__ void __launch_bounds__(128) k_wave_shade(
     }
     nback += __popc(m_end);
     __syncwarp();
-#ifndef RTW_REGEN_THRESHOLD
-#define RTW_REGEN_THRESHOLD 32
-#endif
-#ifndef RTW_CURSOR_PREFETCH
-    if (!static_trips && lane == 0) grabbed = atomicAdd(&ctl->cursor_shade, 32u);
-#endif
-    if (nback >= RTW_REGEN_THRESHOLD) {
-      const uint32_t take = min(nback, 32u);
-      nback -= take;
-      regenerate(f, w, bl, nback + lane, lane < take, next_queue, next_count, out_queue, new_paths);
+    if (lane == 0) grabbed = atomicAdd(&ctl->cursor_shade, 32u);
+    if (nback >= 32u) {
+      nback -= 32u;
+      regenerate(f, w, bl, nback + lane, true, next_queue, next_count, out_queue, new_paths);
     }
   }
   if (nback > 0) regenerate(f, w, bl, lane, lane < nback, next_queue, next_count, out_queue, new_paths);
@@ -558,8 +588,115 @@ __global__ void __launch_bounds__(128) k_wave_shade(
   if (lane == 0 && nseg) atomicAdd(&ctl->segments, (unsigned long long)nseg);  // one world.hit per live entry (lib.rs:102)
 }
 
-// pixel_color = sum over slices, in slice order; pixels of other partitions = 0
-__global__ void k_wave_resolve(FrameDev f, const float4* __restrict__ partial, float* __restrict__ accum) {
+// ---- the fused kernel of one-leaf scenes ------------------------------------------------------------------------------
+// Persistent: grid = SMs x resident blocks.  A lane owns one path at a time and keeps it in registers: camera ray
+// (lib.rs:84-86) -> closest hit over the staged primitive list (hittable/mod.rs:57-69, rtw_traverse.cuh::flat_closest)
+// -> shade / scatter (shade_hit) -> ... until the path ends; then the next sample of its work item, or the next item from
+// the global cursor.  The primitive records, the instance chains and the material of every primitive slot are staged
+// in shared memory once per block; the only global traffic of a frame is the slice sums (16 B per work item).
+// A lane whose path ended restarts at the top of the next trip (all lanes of a warp run the list walk together again);
+// a warp leaves when the cursor is dry and none of its lanes holds a path.
+#ifndef RTW_MEGA_MINBLOCKS
+#define RTW_MEGA_MINBLOCKS 4
+#endif
+#define RTW_MEGA_MAX_OPS 264  // 33 chains x RTW_MAX_CHAIN
+
+struct MegaShared {
+  FlatRecords fr;
+  MaterialRec mat[32];   // material of primitive SLOT k
+  int32_t shade[32];     // its TriShade index or -1
+  uint2 inst_range[40];
+  InstOp inst_ops[RTW_MEGA_MAX_OPS];
+};
+
+__global__ void __launch_bounds__(128, RTW_MEGA_MINBLOCKS) k_mega_flat(SceneDev sc, FrameDev f, float4* __restrict__ partial,
+                                                                      WaveCtl* __restrict__ ctl) {
+  __shared__ MegaShared sh;
+  for (uint32_t i = threadIdx.x; i < sc.flat_count; i += blockDim.x) {
+    const int2 ms = sc.slot_ms[i];
+    sh.mat[i] = sc.materials[ms.x];
+    sh.shade[i] = ms.y;
+  }
+  for (uint32_t i = threadIdx.x; i < sc.num_insts; i += blockDim.x) sh.inst_range[i] = sc.inst_range[i];
+  for (uint32_t i = threadIdx.x; i < sc.num_inst_ops; i += blockDim.x) sh.inst_ops[i] = sc.inst_ops[i];
+  stage_flat(sc, sh.fr);  // ends with __syncthreads()
+  const SharedInst iv{sh.inst_range, sh.inst_ops};
+  const uint32_t nprim = sc.flat_count;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t seed = ((uint64_t)f.seed_hi << 32) | f.seed_lo;
+  uint32_t nseg = 0, npaths = 0;
+  // the lane's path
+  v3 o = mk(0.f, 0.f, 0.f), d = mk(0.f, 0.f, 1.f), T = mk(1.f, 1.f, 1.f), sum = mk(0.f, 0.f, 0.f);
+  float time = 0.f;
+  uint32_t bounce = 0;
+  Item it;
+  it.pixel = it.sample = it.sample_end = it.slice = 0;
+  bool have = false;       // the lane holds a live path
+  bool need_item = true;   // its work item is finished (or it never had one)
+  bool done = false;       // the cursor is dry for this lane
+  for (;;) {
+    // ---- (re)start paths: next sample of the lane's item, or a new item ---------------------------------------------
+    const bool want = !have && !done;
+    if (__any_sync(0xffffffffu, want)) {
+      bool go = want && !need_item;
+      Item nit = it;
+      if (fetch_item(f, ctl, want && need_item, nit)) {
+        it = nit;
+        sum = mk(0.f, 0.f, 0.f);
+        need_item = false;
+        go = true;
+      } else if (want && need_item) {
+        done = true;
+      }
+      if (go) {
+        camera_path(f, it, o, d, time);
+        T = mk(1.f, 1.f, 1.f);
+        bounce = 0;
+        have = true;
+        npaths++;
+      }
+    }
+    if (!__any_sync(0xffffffffu, have)) break;  // every lane is done
+    // ---- closest hit: lib.rs:102 world.hit(r, 0.001, INFINITY) ---------------------------------------------------------
+    float best_t = __int_as_float(0x7f800000);
+    int32_t best_slot;
+    uint32_t best_meta;
+    flat_closest(iv, sh.fr, nprim, o, d, time, 0.001f, have, best_t, best_slot, best_meta);
+    // ---- shade ---------------------------------------------------------------------------------------------------------
+    if (have) {
+      nseg++;
+      v3 L;
+      bool ended;
+      if (best_slot < 0) {  // lib.rs:102-105: miss -> background
+        L = T * f.background;
+        ended = true;
+      } else {
+        ended = shade_hit(sc, iv, f.max_depth, best_meta, sh.mat[best_slot], sh.shade[best_slot], sh.fr.g[best_slot][0],
+                          sh.fr.g[best_slot][1], sh.fr.g[best_slot][2], best_t, seed, it.pixel, it.sample, o, d, time, T,
+                          bounce, L);
+      }
+      if (ended) {
+        sum = sum + L;  // lib.rs:87: pixel_color += sample_ray(..)
+        it.sample += 1;
+        have = false;
+        if (it.sample >= it.sample_end) {  // item done: publish the slice sum
+          publish_item(f, partial, it.pixel, it.slice, sum);
+          need_item = true;
+        }
+      }
+    }
+  }
+  for (int off = 16; off > 0; off >>= 1) {
+    npaths += __shfl_xor_sync(0xffffffffu, npaths, off);
+    nseg += __shfl_xor_sync(0xffffffffu, nseg, off);
+  }
+  if (lane == 0 && npaths) atomicAdd(&ctl->paths, (unsigned long long)npaths);
+  if (lane == 0 && nseg) atomicAdd(&ctl->segments, (unsigned long long)nseg);
+}
+
+// pixel_color = sum over slices, in slice order; pixels of other partitions = 0 (or untouched: skip_unowned)
+__global__ void k_wave_resolve(FrameDev f, const float4* __restrict__ partial) {
+  float* __restrict__ accum = f.accum;
   size_t npix = (size_t)f.width * f.height;
   for (size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pix < npix; pix += (size_t)gridDim.x * blockDim.x) {
     uint32_t x = (uint32_t)(pix % f.width), y_top = (uint32_t)(pix / f.width);
@@ -571,6 +708,8 @@ __global__ void k_wave_resolve(FrameDev f, const float4* __restrict__ partial, f
         float4 s = partial[(size_t)k * f.pix_per_slice + q];
         acc = acc + mk(s.x, s.y, s.z);
       }
+    } else if (f.skip_unowned) {
+      continue;
     }
     accum[3 * pix] = acc.x; accum[3 * pix + 1] = acc.y; accum[3 * pix + 2] = acc.z;
   }
@@ -589,37 +728,98 @@ __global__ void k_resolve_rgb8(const float* __restrict__ accum, size_t n, float 
   }
 }
 
+// ---- host side ---------------------------------------------------------------------------------------------------------
 template <class T>
-int wave_alloc(WaveHost* wh, T** out, size_t count) {
+int wave_alloc(std::vector<void*>* bag, T** out, size_t count) {
   void* p = nullptr;
   cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
   if (e != cudaSuccess) {
     cudaGetLastError();
     return set_error(RTW_ERR_NOMEM, std::string("cudaMalloc (wavefront state) failed: ") + cudaGetErrorString(e));
   }
-  wh->allocs.push_back(p);
+  if (bag) bag->push_back(p);
   *out = (T*)p;
   return RTW_OK;
 }
 
-void wave_release(WaveHost* wh) {
-  for (void* p : wh->allocs) cudaFree(p);
-  wh->allocs.clear();
+void drop_graph(WaveHost* wh) {
+  if (wh->graph_exec) {
+    cudaGraphExecDestroy(wh->graph_exec);
+    count_handle(-1);
+    wh->graph_exec = nullptr;
+  }
+  wh->graph_key = GraphKey();
+}
+
+void release_pool(WaveHost* wh) {
+  drop_graph(wh);  // the graph bakes the pool pointers
+  for (void* p : wh->pool_allocs) cudaFree(p);
+  wh->pool_allocs.clear();
   wh->pool = 0;
-  wh->partial_elems = 0;
+  float4* keep = wh->dev.partial;
+  WaveCtl* ctl = wh->dev.ctl;
+  wh->dev = WaveDev{};
+  wh->dev.partial = keep;
+  wh->dev.ctl = ctl;
+}
+
+void destroy_wave(WaveHost* wh) {
+  if (!wh) return;
+  release_pool(wh);
+  if (wh->partial) cudaFree(wh->partial);
+  if (wh->d_ctl) cudaFree(wh->d_ctl);
+  if (wh->d_frame) cudaFree(wh->d_frame);
+  if (wh->h_frame) cudaFreeHost(wh->h_frame);
+  if (wh->pinned_ctl) cudaFreeHost(wh->pinned_ctl);
+  drop_event(wh->ev_in); drop_event(wh->ev_begin); drop_event(wh->ev_end);
+  drop_event(wh->ring_ev[0]); drop_event(wh->ring_ev[1]);
+  drop_stream(wh->stream);
+  delete wh;
+}
+
+// streams, events, control blocks, occupancy-derived grids: once per scene.  The scene gets the WaveHost only when all
+// of it exists (a failure half way frees what was made).
+int create_wave(rtw_scene* s, WaveHost** out) {
+  WaveHost* wh = new WaveHost();
+  auto fail = [&](int rc) { destroy_wave(wh); return rc; };
+#define RTW_WAVE_TRY(expr)                                         \
+  do {                                                              \
+    cudaError_t _e = (expr);                                        \
+    if (_e != cudaSuccess) return fail(cuda_fail(_e, #expr));       \
+  } while (0)
+  RTW_WAVE_TRY(cudaMallocHost((void**)&wh->pinned_ctl, 3 * sizeof(WaveCtl)));
+  RTW_WAVE_TRY(cudaMallocHost((void**)&wh->h_frame, sizeof(FrameDev)));
+  RTW_WAVE_TRY(cudaMalloc((void**)&wh->d_frame, sizeof(FrameDev)));
+  RTW_WAVE_TRY(cudaMalloc((void**)&wh->d_ctl, sizeof(WaveCtl)));
+  wh->dev.ctl = wh->d_ctl;
+  RTW_WAVE_TRY(new_stream(&wh->stream));
+  RTW_WAVE_TRY(new_event(&wh->ev_in, cudaEventDisableTiming));
+  RTW_WAVE_TRY(new_event(&wh->ev_begin, cudaEventDefault));
+  RTW_WAVE_TRY(new_event(&wh->ev_end, cudaEventDefault));
+  RTW_WAVE_TRY(new_event(&wh->ring_ev[0], cudaEventDisableTiming));
+  RTW_WAVE_TRY(new_event(&wh->ring_ev[1], cudaEventDisableTiming));
+  int nb = 0;
+  const void* kernels[TK_N] = {(const void*)k_wave_traverse<false, false, NODES_PAIR>, (const void*)k_wave_traverse<false, true, NODES_PAIR>,
+                               (const void*)k_wave_traverse<false, false, NODES_WIDE>, (const void*)k_wave_traverse<false, false, NODES_COMPACT>,
+                               (const void*)k_wave_traverse<true, true, NODES_PAIR>, (const void*)k_wave_traverse<true, true, NODES_COMPACT>,
+                               (const void*)k_wave_traverse_flat};
+  for (int k = 0; k < TK_N; ++k) {
+    RTW_WAVE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernels[k], 128, 0));
+    wh->blocks_trav[k] = std::max(nb, 1) * s->num_sms;
+  }
+  RTW_WAVE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wave_shade, 128, 0));
+  wh->blocks_shade = std::max(nb, 1) * s->num_sms;
+  RTW_WAVE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_mega_flat, 128, 0));
+  wh->blocks_mega = std::max(nb, 1) * s->num_sms;
+#undef RTW_WAVE_TRY
+  *out = wh;
+  return RTW_OK;
 }
 
 }  // namespace
 
 void free_wave(rtw_scene* s) {
-  WaveHost* wh = (WaveHost*)s->wave;
-  if (!wh) return;
-  wave_release(wh);
-  if (wh->pinned_ctl) cudaFreeHost(wh->pinned_ctl);
-  if (wh->stream) cudaStreamDestroy(wh->stream);
-  for (auto& ps : wh->pool_stream)
-    if (ps) cudaStreamDestroy(ps);
-  delete wh;
+  destroy_wave((WaveHost*)s->wave);
   s->wave = nullptr;
 }
 
@@ -632,8 +832,8 @@ int resolve_rgb8_device(const float* d_accum, size_t n, uint32_t spp, uint8_t* d
   return RTW_OK;
 }
 
-int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* p, float* d_accum, cudaStream_t st,
-                  rtw_render_stats* stats) {
+int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* p, float* d_accum, cudaStream_t user_stream,
+                  rtw_render_stats* stats, bool skip_unowned) {
   RTW_CUDA_TRY(cudaSetDevice(s->device));
   if (p->width < 2 || p->height < 2) return set_error(RTW_ERR_INVALID, "render: width and height must be >= 2");
   if ((uint64_t)p->width * p->height > 0xFFFFFFFFull) return set_error(RTW_ERR_INVALID, "render: image too large");
@@ -671,31 +871,47 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
   if (f.part_rank >= f.part_count) return set_error(RTW_ERR_INVALID, "render: part_rank >= part_count");
   f.seed_lo = (uint32_t)p->seed;
   f.seed_hi = (uint32_t)(p->seed >> 32);
+  f.skip_unowned = (skip_unowned && f.part_count > 1) ? 1u : 0u;
+  f.accum = d_accum;
   const uint32_t owned_tiles = f.tiles_total > f.part_rank ? (f.tiles_total - f.part_rank + f.part_count - 1) / f.part_count : 0;
   f.pix_per_slice = (unsigned long long)owned_tiles * f.tile_size * f.tile_size;
 
-  // Default pool (measured, profiles/r01_sweeps.txt): every launch of the persistent traversal ends with a drain
-  // in which the SMs wait for the longest rays (~13 us flat scene, ~67 us cow), so launches should be few and
-  // large; the slot state is streamed coalesced (identity mode), it does not need to stay in L2.  2^22 slots
-  // for a flat scene, 2^23 with a hierarchy (104 B per slot: 0.4 / 0.9 GB).
-  uint32_t pool = p->pool_size ? p->pool_size : ((s->dev.num_prims <= 32) ? (1u << 22) : (1u << 23));
-  pool = (pool + 31u) & ~31u;
+  const bool count_trav = (p->flags & RTW_RENDER_COUNT_TRAVERSAL) != 0;
+  const bool time_kernels = (p->flags & RTW_RENDER_TIME_KERNELS) != 0;
+  // a scene that is one leaf (<= 32 primitives, no media) is not walked at all
+  const bool flat_class = s->dev.flat_count > 0 && !s->dev.has_media;
+  bool flat = flat_class;
+  if (const char* e = getenv("RTW_FLAT")) flat = flat && atoi(e) != 0;  // 0: one-leaf scenes through the general walk
+  // ... and runs fused (k_mega_flat) unless the call wants per-kernel times / traversal counters, which only the
+  // wavefront kernels produce (RTW_MEGA=0: A/B against the wavefront)
+  bool mega = flat && !count_trav && !time_kernels && s->dev.num_insts <= 40 && s->dev.num_inst_ops <= RTW_MEGA_MAX_OPS;
+  if (const char* e = getenv("RTW_MEGA")) mega = mega && atoi(e) != 0;
+
+  // ---- slices: from (width, height, samples, scene class) only ---------------------------------------------------------
+  // Enough work items that the last ones to finish are a small fraction of the frame, for one GPU and for an 8-way
+  // tile partition alike.  One-leaf scenes: ~75 k lanes consume items, 16 samples per item are plenty (slice sums
+  // <= 1 GiB).  Hierarchies: the wavefront keeps 2^23 slots busy, a slot runs the samples of its item one after the
+  // other, so coarse items leave the pool idle behind a few long chains (r01: 8-way partition of Cornell, 105 ms at
+  // 64 slices vs 75 ms at 830, ideal 70): ~32 items per slot on one GPU = ~4 under an 8-way partition (slice sums <= 4 GiB).
+  // NEVER derived from the pool size or the partition: the slice count fixes the order of the float additions, and
+  // the frame must have the same bits on 1 or 8 GPUs.
   uint32_t slices = p->slices;
-  if (slices == 0) {  // enough items that the last ones to finish are a small fraction of the frame
-    unsigned long long want = 16ull * pool;
-    unsigned long long per = std::max<unsigned long long>(f.pix_per_slice, 1);
-    // as many slices as it takes for 16 items per slot — a slot runs the samples of its item one after the other,
-    // so coarse items leave a large pool idle behind a few long chains (8-way partition of Cornell: 105 ms at 64
-    // slices vs 72 ms ideal) — bounded by the slice-sum buffer (16 B per item, <= 4 GiB)
-    const unsigned long long cap = std::max<unsigned long long>((256ull << 20) / per, 1ull);
-    slices = (uint32_t)std::min<unsigned long long>((want + per - 1) / per, cap);
+  if (slices == 0) {
+    const unsigned long long full = std::max<unsigned long long>(npix, 1);
+    unsigned long long want, cap;
+    if (flat_class) {
+      want = (nsamp + 15ull) / 16ull;
+      cap = std::max<unsigned long long>((64ull << 20) / full, 1ull);
+    } else {
+      want = (32ull * (1ull << 23) + full - 1) / full;
+      cap = std::max<unsigned long long>((256ull << 20) / full, 1ull);
+    }
+    slices = (uint32_t)std::min(want, cap);
   }
   slices = std::max(1u, std::min(slices, std::max(nsamp, 1u)));
   if (slices > 0xFFFFFFu) return set_error(RTW_ERR_INVALID, "render: too many slices");
   f.slices = slices;
   f.n_items = (nsamp == 0) ? 0ull : f.pix_per_slice * slices;
-  pool = (uint32_t)std::min<unsigned long long>(pool, std::max<unsigned long long>((f.n_items + 31ull) & ~31ull, 32ull));
-  f.pool = pool;
   f.fit32 = (f.n_items < (1ull << 32) && (unsigned long long)nsamp * (slices + 1ull) < (1ull << 32)) ? 1u : 0u;
   f.tile_shift = 0xffffffffu;
   if ((f.tile_size & (f.tile_size - 1u)) == 0u) {
@@ -706,240 +922,192 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
   // ---- scratch (kept on the scene between calls) -------------------------------------------------
   WaveHost* wh = (WaveHost*)s->wave;
   if (!wh) {
-    wh = new WaveHost();
+    int rc = create_wave(s, &wh);
+    if (rc != RTW_OK) return rc;
     s->wave = wh;
-    RTW_CUDA_TRY(cudaMallocHost((void**)&wh->pinned_ctl, 2 * (RTW_MAX_SUBPOOLS + 1) * sizeof(WaveCtl)));
-    RTW_CUDA_TRY(cudaStreamCreateWithFlags(&wh->stream, cudaStreamNonBlocking));
-    for (auto& ps : wh->pool_stream) RTW_CUDA_TRY(cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
-    int nb = 0;
-    const void* kernels[TK_N] = {(const void*)k_wave_traverse<false, false, NODES_PAIR>, (const void*)k_wave_traverse<false, true, NODES_PAIR>,
-                                 (const void*)k_wave_traverse<false, false, NODES_WIDE>, (const void*)k_wave_traverse<false, false, NODES_COMPACT>,
-                                 (const void*)k_wave_traverse<true, true, NODES_PAIR>, (const void*)k_wave_traverse<true, true, NODES_COMPACT>,
-                                 (const void*)k_wave_traverse_flat};
-    for (int k = 0; k < TK_N; ++k) {
-      RTW_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernels[k], 128, 0));
-      wh->blocks_trav[k] = std::max(nb, 1) * s->num_sms;
+  }
+  cudaStream_t st = wh->stream;
+
+  // Wavefront pool (measured, profiles/r01_sweeps.txt): every launch of the persistent traversal ends with a drain in
+  // which the SMs wait for the longest rays (~13 us flat scene, ~67 us cow), so launches should be few and large; the
+  // slot state is streamed coalesced, it does not need to stay in L2.  2^22 slots for a flat scene, 2^23 with a
+  // hierarchy (88 B per slot + two queues: 0.4 / 0.8 GB).  The fused kernel has no pool.
+  uint32_t pool = 0;
+  if (!mega) {
+    pool = p->pool_size ? p->pool_size : (flat_class ? (1u << 22) : (1u << 23));
+    pool = (pool + 31u) & ~31u;
+    pool = (uint32_t)std::min<unsigned long long>(pool, std::max<unsigned long long>((f.n_items + 31ull) & ~31ull, 32ull));
+    if (wh->pool < pool) {  // grow only: a smaller frame reuses the larger arrays
+      release_pool(wh);
+      int rc;
+      WaveDev& w = wh->dev;
+      if ((rc = wave_alloc(&wh->pool_allocs, &w.ray_o, pool)) || (rc = wave_alloc(&wh->pool_allocs, &w.ray_d, pool)) ||
+          (rc = wave_alloc(&wh->pool_allocs, &w.hit, pool)) || (rc = wave_alloc(&wh->pool_allocs, &w.thr, pool)) ||
+          (rc = wave_alloc(&wh->pool_allocs, &w.sum, pool)) || (rc = wave_alloc(&wh->pool_allocs, &w.state, pool)) ||
+          (rc = wave_alloc(&wh->pool_allocs, &w.queue[0], pool)) || (rc = wave_alloc(&wh->pool_allocs, &w.queue[1], pool))) {
+        release_pool(wh);
+        return rc;
+      }
+      wh->pool = pool;
     }
-    RTW_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wave_shade, 128, 0));
-    wh->blocks_shade = std::max(nb, 1) * s->num_sms;
   }
   const size_t partial_elems = slices > 1 ? (size_t)slices * f.pix_per_slice : 0;
-  if (wh->pool != pool || wh->partial_elems < partial_elems) {
-    wave_release(wh);
-    int rc;
-    WaveDev& w = wh->dev;
-    if ((rc = wave_alloc(wh, &w.ray_o, pool))) return rc;
-    if ((rc = wave_alloc(wh, &w.ray_d, pool))) return rc;
-    if ((rc = wave_alloc(wh, &w.hit, pool))) return rc;
-    if ((rc = wave_alloc(wh, &w.thr, pool))) return rc;
-    if ((rc = wave_alloc(wh, &w.sum, pool))) return rc;
-    if ((rc = wave_alloc(wh, &w.state, pool))) return rc;
-    if ((rc = wave_alloc(wh, &w.queue[0], pool))) return rc;
-    if ((rc = wave_alloc(wh, &w.queue[1], pool))) return rc;
-    if ((rc = wave_alloc(wh, &w.partial, partial_elems))) return rc;
-    if ((rc = wave_alloc(wh, &w.ctl, RTW_MAX_SUBPOOLS + 1))) return rc;
-    wh->pool = pool;
+  if (wh->partial_elems < partial_elems) {
+    drop_graph(wh);
+    if (wh->partial) cudaFree(wh->partial);
+    wh->partial = nullptr;
+    wh->partial_elems = 0;
+    int rc = wave_alloc((std::vector<void*>*)nullptr, &wh->partial, partial_elems);
+    if (rc) return rc;
     wh->partial_elems = partial_elems;
   }
-  WaveDev& w = wh->dev;
+  wh->dev.partial = wh->partial;
+  wh->dev.ctl = wh->d_ctl;
+  wh->dev.slot_count = pool;
+  const WaveDev w = wh->dev;
 
   // The 4-wide walk (SceneDev::nodes4) halves the dependent node fetches but moves MORE bytes (it fetches the boxes
-  // below a child whose own box the ray misses).  Measured r01: no gain on C5 (257 vs 253 ms) — that traversal sits at
-  // the random-gather bandwidth of the memory system (tools/gather_peak.cu: 1.3 TB/s beyond L2), not at its latency —
-  // and 5-17 % slower on cache-resident scenes.  Off unless RTW_WIDE=1 (parity-tested).
+  // below a child whose own box the ray misses).  Measured r01: no gain on C5 — that traversal sits at the
+  // random-gather bandwidth of the memory system, not at its latency — and 5-17 % slower on cache-resident scenes.
+  // Built and used only with RTW_WIDE=1 (parity-tested).
   bool wide = false;
   if (const char* e = getenv("RTW_WIDE"))
-    wide = atoi(e) != 0 && !s->dev.has_media && 3u * (s->bvh_height / 2u + 1u) + 2u <= RTW_STACK_SIZE;
-  const bool count_trav = (p->flags & RTW_RENDER_COUNT_TRAVERSAL) != 0;
-  const bool time_kernels = (p->flags & 2u) != 0;
+    wide = atoi(e) != 0 && s->dev.nodes4 != nullptr && !s->dev.has_media && 3u * (s->bvh_height / 2u + 1u) + 2u <= RTW_STACK_SIZE;
   // compact pairs exist only when rtw_build found the hierarchy too large for the caches (rtw_bvh.cu)
   const bool compact = s->dev.nodes_c != nullptr && !s->dev.has_media;
-  // a scene that is one leaf (<= 32 primitives, no media) is not walked at all (RTW_FLAT=0: use the general kernel)
-  bool flat = s->dev.flat_count > 0 && !s->dev.has_media;
-  if (const char* e = getenv("RTW_FLAT")) flat = flat && atoi(e) != 0;
   const TravKind kind = count_trav ? (compact ? TK_COUNT_COMPACT : TK_COUNT)
                                    : (s->dev.has_media ? TK_MEDIA : (flat ? TK_FLAT : (compact ? TK_COMPACT : (wide ? TK_WIDE : TK_PAIR))));
-  auto launch_traverse = [&](cudaStream_t sk, const WaveDev& wd, uint32_t parity, int grid) {
+  const FrameDev* dfp = wh->d_frame;
+  auto launch_traverse = [&](uint32_t parity, int grid) {
     switch (kind) {
-      case TK_PAIR: k_wave_traverse<false, false, NODES_PAIR><<<grid, 128, 0, sk>>>(s->dev, wd, parity, f.seed_lo, f.seed_hi); break;
-      case TK_MEDIA: k_wave_traverse<false, true, NODES_PAIR><<<grid, 128, 0, sk>>>(s->dev, wd, parity, f.seed_lo, f.seed_hi); break;
-      case TK_WIDE: k_wave_traverse<false, false, NODES_WIDE><<<grid, 128, 0, sk>>>(s->dev, wd, parity, f.seed_lo, f.seed_hi); break;
-      case TK_COMPACT: k_wave_traverse<false, false, NODES_COMPACT><<<grid, 128, 0, sk>>>(s->dev, wd, parity, f.seed_lo, f.seed_hi); break;
-      case TK_COUNT: k_wave_traverse<true, true, NODES_PAIR><<<grid, 128, 0, sk>>>(s->dev, wd, parity, f.seed_lo, f.seed_hi); break;
-      case TK_FLAT: k_wave_traverse_flat<<<grid, 128, 0, sk>>>(s->dev, wd, parity, f.seed_lo, f.seed_hi); break;
-      default: k_wave_traverse<true, true, NODES_COMPACT><<<grid, 128, 0, sk>>>(s->dev, wd, parity, f.seed_lo, f.seed_hi); break;
+      case TK_PAIR: k_wave_traverse<false, false, NODES_PAIR><<<grid, 128, 0, st>>>(s->dev, dfp, w, parity); break;
+      case TK_MEDIA: k_wave_traverse<false, true, NODES_PAIR><<<grid, 128, 0, st>>>(s->dev, dfp, w, parity); break;
+      case TK_WIDE: k_wave_traverse<false, false, NODES_WIDE><<<grid, 128, 0, st>>>(s->dev, dfp, w, parity); break;
+      case TK_COMPACT: k_wave_traverse<false, false, NODES_COMPACT><<<grid, 128, 0, st>>>(s->dev, dfp, w, parity); break;
+      case TK_COUNT: k_wave_traverse<true, true, NODES_PAIR><<<grid, 128, 0, st>>>(s->dev, dfp, w, parity); break;
+      case TK_FLAT: k_wave_traverse_flat<<<grid, 128, 0, st>>>(s->dev, dfp, w, parity); break;
+      default: k_wave_traverse<true, true, NODES_COMPACT><<<grid, 128, 0, st>>>(s->dev, dfp, w, parity); break;
     }
   };
-  // All work runs on an internal stream ordered after the caller's stream; the call returns only after
-  // that stream has drained, so the caller's stream order is preserved on both sides.
-  cudaStream_t user_stream = st;
-  st = wh->stream;
-  cudaEvent_t ev_in, ev_begin, ev_end;
-  RTW_CUDA_TRY(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
-  RTW_CUDA_TRY(cudaEventRecord(ev_in, user_stream));
-  RTW_CUDA_TRY(cudaStreamWaitEvent(st, ev_in, 0));
-  RTW_CUDA_TRY(cudaEventCreate(&ev_begin));
-  RTW_CUDA_TRY(cudaEventCreate(&ev_end));
-  std::vector<cudaEvent_t> kev;  // begin/end pairs: traverse, shade, traverse, shade ...
-  uint32_t launches = 0, iterations = 0;
 
-  // Sub-pools: the slot range is split into K independent halves/quarters, each with its own queues,
-  // counters and stream.  Their kernels depend only on their own predecessor, so the ramp-up and the
-  // tail of one sub-pool's persistent kernel (~15 us per launch, measured by the pool-size sweep in
-  // profiles/) overlap the body of another's, and latency-bound shading overlaps issue-bound traversal.
-  // (r01: K = 2 gained 4 % while every iteration compacted into queues; with identity slots and 2^22+ pools one
-  // pool is fastest — K = 1 / 2 / 3: cow 3507 / 3454 / 3347 Mrays/s, Cornell 7124 / 7113 / 6840.  Kept for experiments.)
-  uint32_t K = 1;
-  if (!count_trav && !time_kernels && pool >= (1u << 16)) {
-    if (const char* e = getenv("RTW_SUBPOOLS")) K = (uint32_t)std::min(std::max(atoi(e), 1), RTW_MAX_SUBPOOLS);
-  }
-  WaveDev wk[RTW_MAX_SUBPOOLS];
-  {
-    uint32_t per = ((pool / K) + 31u) & ~31u, base = 0;
-    for (uint32_t k = 0; k < K; ++k) {
-      wk[k] = w;
-      wk[k].ctl = w.ctl + k;
-      wk[k].item_cursor = &w.ctl[RTW_MAX_SUBPOOLS].item_cursor;
-      wk[k].exhausted = &w.ctl[RTW_MAX_SUBPOOLS].exhausted;
-      wk[k].slot_base = base;
-      wk[k].slot_count = (k + 1 == K) ? pool - base : std::min(per, pool - base);
-      wk[k].queue[0] = w.queue[0] + base;
-      wk[k].queue[1] = w.queue[1] + base;
-      base += wk[k].slot_count;
-    }
-  }
-  RTW_CUDA_TRY(cudaEventRecord(ev_begin, st));
-  RTW_CUDA_TRY(cudaMemsetAsync(w.ctl, 0, (RTW_MAX_SUBPOOLS + 1) * sizeof(WaveCtl), st));
-  if (slices == 1) RTW_CUDA_TRY(cudaMemsetAsync(d_accum, 0, npix * 3 * sizeof(float), st));
-  if (f.n_items > 0) {
+  // All work runs on an internal stream ordered after the caller's stream; the call returns only after that stream has
+  // drained, so the caller's stream order is preserved on both sides.
+  RTW_CUDA_TRY(cudaEventRecord(wh->ev_in, user_stream));
+  RTW_CUDA_TRY(cudaStreamWaitEvent(st, wh->ev_in, 0));
+  EventBag kev;  // begin/end pairs of the instrumented path: traverse, shade, traverse, shade ...
+  uint32_t launches = 0, iterations = 0;
+  const char* fault = getenv("RTW_FAULT_INJECT");  // tests: "capture" fails inside the graph capture, "launch" launches an invalid grid
+
+  RTW_CUDA_TRY(cudaEventRecord(wh->ev_begin, st));
+  RTW_CUDA_TRY(cudaMemsetAsync(wh->d_ctl, 0, sizeof(WaveCtl), st));
+  if (slices == 1 && !f.skip_unowned) RTW_CUDA_TRY(cudaMemsetAsync(d_accum, 0, npix * 3 * sizeof(float), st));
+  if (f.n_items > 0 && mega) {
+    // ---- one-leaf scene: the whole frame is one launch ---------------------------------------------------------------
+    const unsigned long long need_blocks = (f.n_items + 127ull) / 128ull;
+    int grid = (int)std::min<unsigned long long>((unsigned long long)wh->blocks_mega, std::max<unsigned long long>(need_blocks, 1ull));
+    if (fault && !strcmp(fault, "launch")) grid = -1;
+    k_mega_flat<<<grid, 128, 0, st>>>(s->dev, f, wh->partial, wh->d_ctl);
+    RTW_CUDA_TRY(cudaGetLastError());
+    launches++;
+    iterations = 1;
+    pool = (uint32_t)grid * 128u;
+  } else if (f.n_items > 0) {
+    *wh->h_frame = f;
+    RTW_CUDA_TRY(cudaMemcpyAsync(wh->d_frame, wh->h_frame, sizeof(FrameDev), cudaMemcpyHostToDevice, st));
     if (!count_trav && !time_kernels) {
-      // ---- product path: per sub-pool a CUDA graph of BATCH iterations, launched back to back; the host
-      // looks at the live count of round i-1 while round i is already running.
-      // BATCH is even (the queue parity is back to 0 after every batch).  The termination check lags one round, so a
-      // frame runs up to 2 x BATCH - 1 empty iterations at its end: 16 for long frames, 4 for short ones (fewer than
-      // two work items per slot: a ~50-iteration frame of a few ms, where 31 empty launch pairs would be a third of it).
-      const int BATCH = (f.n_items >= 2ull * pool) ? 16 : 4;
+      // ---- product path: a CUDA graph of BATCH iterations, launched back to back; the host looks at the live count
+      // of round i-1 while round i is already running.  BATCH is even (the queue parity is back to 0 after every
+      // batch).  The termination check lags one round, so a frame runs up to 2 x BATCH - 1 empty iterations at its
+      // end: 16 for long frames, 4 for short ones (fewer than two work items per slot).
+      GraphKey key;
+      key.kind = (int)kind;
+      key.batch = (f.n_items >= 2ull * pool) ? 16 : 4;
       // a small pool does not need the full persistent grid: fewer blocks launch (and drain) faster
       const int need_blocks = (int)((pool + 127u) / 128u);
-      int grid_t = std::min(wh->blocks_trav[kind], std::max(need_blocks, 1));
-      int grid_s = std::min(wh->blocks_shade, std::max(need_blocks, 1));
-  
-      cudaEvent_t ev_fork, ev_join[RTW_MAX_SUBPOOLS], ring_ev[RTW_MAX_SUBPOOLS][2];
-      cudaGraph_t graph[RTW_MAX_SUBPOOLS];
-      cudaGraphExec_t exec[RTW_MAX_SUBPOOLS];
-      RTW_CUDA_TRY(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-      RTW_CUDA_TRY(cudaEventRecord(ev_fork, st));
-      for (uint32_t k = 0; k < K; ++k) {
-        cudaStream_t sk = wh->pool_stream[k];
-        RTW_CUDA_TRY(cudaEventCreateWithFlags(&ev_join[k], cudaEventDisableTiming));
-        for (auto& e : ring_ev[k]) RTW_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        RTW_CUDA_TRY(cudaStreamWaitEvent(sk, ev_fork, 0));
-        k_wave_init<<<(wk[k].slot_count + 127) / 128, 128, 0, sk>>>(s->dev, f, wk[k]);
-        launches++;
-        RTW_CUDA_TRY(cudaStreamBeginCapture(sk, cudaStreamCaptureModeThreadLocal));
-        for (int b = 0; b < BATCH; ++b) {
-          launch_traverse(sk, wk[k], (uint32_t)(b & 1), grid_t);
-          k_wave_shade<<<grid_s, 128, 0, sk>>>(s->dev, f, wk[k], d_accum, (uint32_t)(b & 1));
+      key.grid_t = std::min(wh->blocks_trav[kind], std::max(need_blocks, 1));
+      key.grid_s = std::min(wh->blocks_shade, std::max(need_blocks, 1));
+      key.pool = pool;
+      if (!(wh->graph_exec && wh->graph_key == key)) {
+        drop_graph(wh);
+        cudaGraph_t graph = nullptr;
+        RTW_CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        for (int b = 0; b < key.batch; ++b) {
+          launch_traverse((uint32_t)(b & 1), key.grid_t);
+          k_wave_shade<<<key.grid_s, 128, 0, st>>>(s->dev, dfp, w, (uint32_t)(b & 1));
         }
-        RTW_CUDA_TRY(cudaStreamEndCapture(sk, &graph[k]));
-        RTW_CUDA_TRY(cudaGraphInstantiate(&exec[k], graph[k], 0));
+        cudaError_t ce = cudaStreamEndCapture(st, &graph);  // always ends the capture, whatever happened inside
+        if (ce == cudaSuccess && fault && !strcmp(fault, "capture")) ce = cudaErrorUnknown;
+        cudaGraphExec_t exec = nullptr;
+        if (ce == cudaSuccess) ce = cudaGraphInstantiate(&exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) return cuda_fail(ce, "graph capture of the wavefront batch");
+        count_handle(1);
+        wh->graph_exec = exec;
+        wh->graph_key = key;
       }
-      bool done[RTW_MAX_SUBPOOLS] = {false, false, false, false};
+      k_wave_init<<<(pool + 127) / 128, 128, 0, st>>>(s->dev, dfp, w);
+      launches++;
       for (uint32_t i = 0;; ++i) {
-        for (uint32_t k = 0; k < K; ++k) {
-          if (done[k]) continue;
-          cudaStream_t sk = wh->pool_stream[k];
-          RTW_CUDA_TRY(cudaGraphLaunch(exec[k], sk));
-          RTW_CUDA_TRY(cudaMemcpyAsync(&wh->pinned_ctl[2 * k + (i & 1)], w.ctl + k, sizeof(WaveCtl), cudaMemcpyDeviceToHost, sk));
-          RTW_CUDA_TRY(cudaEventRecord(ring_ev[k][i & 1], sk));
-          launches += 2 * BATCH;
-        }
-        iterations += BATCH;
+        RTW_CUDA_TRY(cudaGraphLaunch(wh->graph_exec, st));
+        RTW_CUDA_TRY(cudaMemcpyAsync(&wh->pinned_ctl[i & 1], wh->d_ctl, sizeof(WaveCtl), cudaMemcpyDeviceToHost, st));
+        RTW_CUDA_TRY(cudaEventRecord(wh->ring_ev[i & 1], st));
+        launches += 2 * key.batch;
+        iterations += key.batch;
         if (i >= 1) {
-          bool all = true;
-          for (uint32_t k = 0; k < K; ++k) {
-            if (!done[k]) {
-              RTW_CUDA_TRY(cudaEventSynchronize(ring_ev[k][(i - 1) & 1]));
-              if (wh->pinned_ctl[2 * k + ((i - 1) & 1)].count[0] == 0) done[k] = true;  // absorbing: queue mode, no live path, no item left
-            }
-            all = all && done[k];
-          }
-          if (all) break;
+          RTW_CUDA_TRY(cudaEventSynchronize(wh->ring_ev[(i - 1) & 1]));
+          if (wh->pinned_ctl[(i - 1) & 1].count[0] == 0) break;  // absorbing: queue mode, no live path, no item left
         }
       }
-      for (uint32_t k = 0; k < K; ++k) {
-        RTW_CUDA_TRY(cudaEventRecord(ev_join[k], wh->pool_stream[k]));
-        RTW_CUDA_TRY(cudaStreamWaitEvent(st, ev_join[k], 0));
-        cudaEventDestroy(ev_join[k]);
-        for (auto& e : ring_ev[k]) cudaEventDestroy(e);
-        cudaGraphExecDestroy(exec[k]);
-        cudaGraphDestroy(graph[k]);
-      }
-      cudaEventDestroy(ev_fork);
     } else {
-      // ---- instrumented path (traversal counters / per-kernel CUDA events): one pool, plain launches
-      k_wave_init<<<(pool + 127) / 128, 128, 0, st>>>(s->dev, f, wk[0]);
+      // ---- instrumented path (traversal counters / per-kernel CUDA events): plain launches
+      k_wave_init<<<(pool + 127) / 128, 128, 0, st>>>(s->dev, dfp, w);
       launches++;
       uint32_t parity = 0;
       const int batch = 8;
       for (;;) {
         for (int b = 0; b < batch; ++b) {
+          cudaEvent_t e4[4] = {nullptr, nullptr, nullptr, nullptr};
           if (time_kernels) {
-            cudaEvent_t e4[4];
-            for (auto& e : e4) { RTW_CUDA_TRY(cudaEventCreate(&e)); kev.push_back(e); }
+            for (auto& e : e4) RTW_CUDA_TRY(kev.add(&e));
             RTW_CUDA_TRY(cudaEventRecord(e4[0], st));
           }
-          launch_traverse(st, wk[0], parity, wh->blocks_trav[kind]);
+          launch_traverse(parity, wh->blocks_trav[kind]);
           if (time_kernels) {
-            RTW_CUDA_TRY(cudaEventRecord(kev[kev.size() - 3], st));
-            RTW_CUDA_TRY(cudaEventRecord(kev[kev.size() - 2], st));
+            RTW_CUDA_TRY(cudaEventRecord(e4[1], st));
+            RTW_CUDA_TRY(cudaEventRecord(e4[2], st));
           }
-          k_wave_shade<<<wh->blocks_shade, 128, 0, st>>>(s->dev, f, wk[0], d_accum, parity);
-          if (time_kernels) RTW_CUDA_TRY(cudaEventRecord(kev[kev.size() - 1], st));
+          k_wave_shade<<<wh->blocks_shade, 128, 0, st>>>(s->dev, dfp, w, parity);
+          if (time_kernels) RTW_CUDA_TRY(cudaEventRecord(e4[3], st));
           parity ^= 1;
           launches += 2;
           iterations++;
         }
-        RTW_CUDA_TRY(cudaMemcpyAsync(wh->pinned_ctl, w.ctl, sizeof(WaveCtl), cudaMemcpyDeviceToHost, st));
+        RTW_CUDA_TRY(cudaMemcpyAsync(wh->pinned_ctl, wh->d_ctl, sizeof(WaveCtl), cudaMemcpyDeviceToHost, st));
         RTW_CUDA_TRY(cudaStreamSynchronize(st));
         if (wh->pinned_ctl->count[parity] == 0) break;
       }
     }
   }
-  if (slices > 1 || f.n_items == 0) {
-    if (f.n_items == 0 && slices > 1) RTW_CUDA_TRY(cudaMemsetAsync(w.partial, 0, partial_elems * sizeof(float4), st));
-    if (slices > 1) {
-      k_wave_resolve<<<std::min<uint32_t>((uint32_t)((npix + 255) / 256), 8u * (uint32_t)s->num_sms), 256, 0, st>>>(f, w.partial, d_accum);
-      launches++;
-    }
+  if (slices > 1) {
+    if (f.n_items == 0 && partial_elems) RTW_CUDA_TRY(cudaMemsetAsync(wh->partial, 0, partial_elems * sizeof(float4), st));
+    k_wave_resolve<<<std::min<uint32_t>((uint32_t)((npix + 255) / 256), 8u * (uint32_t)s->num_sms), 256, 0, st>>>(f, wh->partial);
+    launches++;
   }
   RTW_CUDA_TRY(cudaGetLastError());
-  RTW_CUDA_TRY(cudaEventRecord(ev_end, st));
-  RTW_CUDA_TRY(cudaMemcpyAsync(wh->pinned_ctl, w.ctl, RTW_MAX_SUBPOOLS * sizeof(WaveCtl), cudaMemcpyDeviceToHost, st));
+  RTW_CUDA_TRY(cudaEventRecord(wh->ev_end, st));
+  RTW_CUDA_TRY(cudaMemcpyAsync(&wh->pinned_ctl[2], wh->d_ctl, sizeof(WaveCtl), cudaMemcpyDeviceToHost, st));
   RTW_CUDA_TRY(cudaStreamSynchronize(st));
-  WaveCtl total;
-  memset(&total, 0, sizeof(total));
-  for (uint32_t k = 0; k < K; ++k) {
-    total.segments += wh->pinned_ctl[k].segments;
-    total.paths += wh->pinned_ctl[k].paths;
-    total.pairs += wh->pinned_ctl[k].pairs;
-    total.prims += wh->pinned_ctl[k].prims;
-    total.prim_bytes += wh->pinned_ctl[k].prim_bytes;
-  }
+  const WaveCtl total = wh->pinned_ctl[2];
   float ms = 0.f;
-  cudaEventElapsedTime(&ms, ev_begin, ev_end);
-  cudaEventDestroy(ev_in);
-  cudaEventDestroy(ev_begin);
-  cudaEventDestroy(ev_end);
+  cudaEventElapsedTime(&ms, wh->ev_begin, wh->ev_end);
   float ms_t = 0.f, ms_s = 0.f;
-  for (size_t i = 0; i + 3 < kev.size(); i += 4) {
+  for (size_t i = 0; i + 3 < kev.v.size(); i += 4) {
     float a = 0.f, b = 0.f;
-    cudaEventElapsedTime(&a, kev[i], kev[i + 1]);
-    cudaEventElapsedTime(&b, kev[i + 2], kev[i + 3]);
+    cudaEventElapsedTime(&a, kev.v[i], kev.v[i + 1]);
+    cudaEventElapsedTime(&b, kev.v[i + 2], kev.v[i + 3]);
     ms_t += a;
     ms_s += b;
   }
-  for (auto& e : kev) cudaEventDestroy(e);
   if (stats) {
     memset(stats, 0, sizeof(*stats));
     stats->segments = total.segments;
@@ -954,7 +1122,8 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
     stats->ms_render = ms;
     stats->ms_traverse = ms_t;
     stats->ms_shade = ms_s;
-    stats->node_record_bytes = compact ? 32.f : (wide ? 128.f : 64.f);
+    stats->node_record_bytes = mega ? 0.f : (compact ? 32.f : (wide ? 128.f : 64.f));
+    stats->fused = mega ? 1u : 0u;
   }
   return RTW_OK;
 }

@@ -56,6 +56,7 @@ struct rtw_scene {
 
   // ---- device buffers (owned) -----------------------------------------------------------------
   std::vector<void*> allocations;
+  std::vector<size_t> allocation_bytes;  // parallel to `allocations` (rtw_scene_clone copies them peer to peer)
   uint64_t device_bytes = 0;
   rtw::SceneDev dev{};
   float root_box[6] = {0, 0, 0, 0, 0, 0};
@@ -63,6 +64,16 @@ struct rtw_scene {
 
   // render scratch kept between calls (rtw_render.cu)
   void* wave = nullptr;
+  // rtw_render (host buffers): frame buffer on the device + pinned staging, kept between calls (grow only)
+  float* io_frame = nullptr;
+  float* io_pinned = nullptr;
+  size_t io_bytes = 0;
+  // multi-GPU (rtw_render_params::gpus > 1): replicas of this scene on the other devices, created on first use;
+  // staging[i] = device memory of THIS scene's device for replica i's frame when peer stores are not possible
+  std::vector<rtw_scene*> replicas;
+  std::vector<float*> staging;
+  size_t staging_bytes = 0;
+  bool is_replica = false;
 };
 
 namespace rtw {
@@ -75,9 +86,20 @@ void free_scene_device(rtw_scene* s);
 int trace_closest_device(rtw_scene* s, const rtw_ray* d_rays, uint64_t n, rtw_hit* d_hits, int mode, cudaStream_t st);
 
 // rtw_render.cu
+// skip_unowned: pixels outside this call's tile partition are left untouched instead of being written as 0
+// (the multi-GPU path: every replica stores its own tiles into ONE frame, rtw_multi.cu)
 int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* p, float* d_accum, cudaStream_t st,
-                  rtw_render_stats* stats);
+                  rtw_render_stats* stats, bool skip_unowned = false);
 void free_wave(rtw_scene* s);
+// handles (events, streams, graphs) this library has created and not yet destroyed: the leak check of the tests
+int live_handles();
+void count_handle(int delta);
+
+// rtw_multi.cu: one frame over `gpus` devices, replicas on first use; the frame lands in d_frame (memory of s->device)
+int render_multi_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* p, float* d_frame,
+                        rtw_render_stats* stats);
+int clone_scene(const rtw_scene* src, int device, rtw_scene** out);
+void free_replicas(rtw_scene* s);
 int resolve_rgb8_device(const float* d_accum, size_t n, uint32_t spp, uint8_t* d_rgb8, cudaStream_t st);
 
 }  // namespace rtw

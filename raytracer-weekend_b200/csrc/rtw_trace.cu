@@ -106,7 +106,7 @@ int trace_closest_device(rtw_scene* s, const rtw_ray* d_rays, uint64_t n, rtw_hi
     // same switch as the renderer (rtw_render.cu): the 4-wide walk is an experiment, off unless RTW_WIDE=1
     bool wide = false;
     if (const char* e = getenv("RTW_WIDE"))
-      wide = atoi(e) != 0 && !s->dev.has_media && 3u * (s->bvh_height / 2u + 1u) + 2u <= RTW_STACK_SIZE;
+      wide = atoi(e) != 0 && s->dev.nodes4 != nullptr && !s->dev.has_media && 3u * (s->bvh_height / 2u + 1u) + 2u <= RTW_STACK_SIZE;
     bool flat = s->dev.flat_count > 0 && !s->dev.has_media;
     if (const char* e = getenv("RTW_FLAT")) flat = flat && atoi(e) != 0;
     uint32_t* cursor = nullptr;

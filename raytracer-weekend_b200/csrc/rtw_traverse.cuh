@@ -494,10 +494,56 @@ __device__ __forceinline__ void stage_flat(const SceneDev& sc, FlatRecords& fr) 
   __syncthreads();
 }
 
+// The closest hit of one ray over the staged records: every lane of the warp walks the list together (call with the
+// whole warp; `active` = this lane holds a ray).  best_t comes in as the ray's t_max.
+template <class IV>
+__device__ __forceinline__ void flat_closest(const IV& iv, const FlatRecords& fr, uint32_t nprim, v3 o, v3 d, float time,
+                                             float t_min, bool active, float& best_t, int32_t& best_slot,
+                                             uint32_t& best_meta) {
+  int32_t best_id = -2;
+  uint32_t cur_inst = 0;
+  best_slot = -1;
+  best_meta = 0;
+  v3 oi = o, di = d;
+  for (uint32_t k = 0; k < nprim; ++k) {  // warp-uniform
+    const uint32_t pm = fr.meta[k];
+    const uint32_t type = pm & 7u, inst = pm >> RTW_META_TYPE_BITS;
+    if (inst != cur_inst) {
+      oi = o; di = d;
+      if (inst != 0) ray_to_instance_iv(iv, inst, oi, di);
+      cur_inst = inst;
+    }
+    const float4 g0 = fr.g[k][0];
+    float t, a, b;
+    bool hit;
+    if (type == PT_RECT_XZ)
+      hit = rect_t_perm(oi.x, oi.z, oi.y, di.x, di.z, di.y, t_min, best_t, g0, fr.g[k][1].x, t);
+    else if (type == PT_RECT_XY)
+      hit = rect_t_perm(oi.x, oi.y, oi.z, di.x, di.y, di.z, t_min, best_t, g0, fr.g[k][1].x, t);
+    else if (type == PT_RECT_YZ)
+      hit = rect_t_perm(oi.y, oi.z, oi.x, di.y, di.z, di.x, t_min, best_t, g0, fr.g[k][1].x, t);
+    else if (type <= PT_MSPHERE) {
+      v3 center = mk(g0.x, g0.y, g0.z);
+      if (type == PT_MSPHERE) center = moving_center(g0, fr.g[k][1], fr.g[k][2], time);
+      hit = sphere_t(oi, di, t_min, best_t, center, g0.w, t);
+    } else {
+      hit = tri_t(oi, di, t_min, best_t, g0, fr.g[k][1], fr.g[k][2], t, a, b);
+    }
+    if (hit && active) {
+      if (best_slot < 0 || t < best_t) {
+        best_t = t; best_slot = (int32_t)k; best_meta = pm; best_id = fr.prim[k];
+      } else if (fr.prim[k] > best_id) {  // t == best_t: the later primitive of the canonical order wins
+        best_slot = (int32_t)k; best_meta = pm; best_id = fr.prim[k];
+      }
+    }
+  }
+}
+
 template <class IO>
 __device__ __forceinline__ void traverse_flat(const SceneDev& sc, const FlatRecords& fr, IO& io, uint32_t count, uint32_t* cursor) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t nprim = sc.flat_count;
+  const GlobalInst iv{sc.inst_range, sc.inst_ops};
   for (;;) {
     uint32_t base = 0;
     if (lane == 0) base = atomicAdd(cursor, 32u);
@@ -509,41 +555,9 @@ __device__ __forceinline__ void traverse_flat(const SceneDev& sc, const FlatReco
     int32_t slot0 = -1;
     bool resumed = false;
     const bool active = index < count && io.load(index, o, d, time, t_min, best_t, slot0, resumed);
-    int32_t best_slot = -1, best_id = -2;
-    uint32_t best_meta = 0, cur_inst = 0;
-    v3 oi = o, di = d;
-    for (uint32_t k = 0; k < nprim; ++k) {  // warp-uniform
-      const uint32_t pm = fr.meta[k];
-      const uint32_t type = pm & 7u, inst = pm >> RTW_META_TYPE_BITS;
-      if (inst != cur_inst) {
-        oi = o; di = d;
-        if (inst != 0) ray_to_instance(sc, inst, oi, di);
-        cur_inst = inst;
-      }
-      const float4 g0 = fr.g[k][0];
-      float t, a, b;
-      bool hit;
-      if (type == PT_RECT_XZ)
-        hit = rect_t_perm(oi.x, oi.z, oi.y, di.x, di.z, di.y, t_min, best_t, g0, fr.g[k][1].x, t);
-      else if (type == PT_RECT_XY)
-        hit = rect_t_perm(oi.x, oi.y, oi.z, di.x, di.y, di.z, t_min, best_t, g0, fr.g[k][1].x, t);
-      else if (type == PT_RECT_YZ)
-        hit = rect_t_perm(oi.y, oi.z, oi.x, di.y, di.z, di.x, t_min, best_t, g0, fr.g[k][1].x, t);
-      else if (type <= PT_MSPHERE) {
-        v3 center = mk(g0.x, g0.y, g0.z);
-        if (type == PT_MSPHERE) center = moving_center(g0, fr.g[k][1], fr.g[k][2], time);
-        hit = sphere_t(oi, di, t_min, best_t, center, g0.w, t);
-      } else {
-        hit = tri_t(oi, di, t_min, best_t, g0, fr.g[k][1], fr.g[k][2], t, a, b);
-      }
-      if (hit && active) {
-        if (best_slot < 0 || t < best_t) {
-          best_t = t; best_slot = (int32_t)k; best_meta = pm; best_id = fr.prim[k];
-        } else if (fr.prim[k] > best_id) {  // t == best_t: the later primitive of the canonical order wins
-          best_slot = (int32_t)k; best_meta = pm; best_id = fr.prim[k];
-        }
-      }
-    }
+    int32_t best_slot;
+    uint32_t best_meta;
+    flat_closest(iv, fr, nprim, o, d, time, t_min, active, best_t, best_slot, best_meta);
     if (active) io.store(index, o, d, time, best_slot, best_t, best_meta);
   }
 }

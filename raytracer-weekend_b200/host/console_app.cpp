@@ -1,7 +1,7 @@
 // console_app with a `--backend cuda` switch: the C++ mirror of console_app/src/main.rs.
 //
 //   console_app [--width|-w 400] [--aspect-ratio|-a 1.7777778] [--samples-per-pixel|-s 100]
-//               [--backend cuda] [--seed N] [--device D] [--lib PATH] [--out-dir render] <scene>
+//               [--backend cuda] [--gpus N] [--seed N] [--device D] [--lib PATH] [--out-dir render] <scene>
 //
 // Same flow as main.rs:28-96: image_height = round(width / aspect_ratio); Scene::generate with
 // aspect = width/height; one Raytracer per camera; divide by spp, gamma 2, clamp, u8; save
@@ -66,6 +66,7 @@ bool save_png(const std::string& path, const uint8_t* rgb, uint32_t w, uint32_t 
           "  -a, --aspect-ratio <ASPECT_RATIO>      [default: 1.7777778]\n"
           "  -s, --samples-per-pixel <SPP>          [default: 100]\n"
           "      --backend <cuda>                   [default: cuda]\n"
+          "      --gpus <N>                         spread every frame over N GPUs of the box [default: 1]\n"
           "      --seed <N>  --device <D>  --lib <librtw_cuda.so>  --out-dir <DIR>\n"
           "      --progress-out <FILE>   also write the frames as a ProgressMessage stream (postcard + COBS,\n"
           "                              the wire format of discovery_host_receiver)\n"
@@ -83,6 +84,7 @@ int main(int argc, char** argv) {
   std::string backend = "cuda", scene, out_dir = "render", lib, progress_out;
   uint64_t seed = 1;
   int device = 0;
+  uint32_t gpus = 1;
   for (int i = 1; i < argc; ++i) {
     std::string a = argv[i];
     auto val = [&]() -> std::string {
@@ -95,6 +97,7 @@ int main(int argc, char** argv) {
     else if (a == "--backend") backend = val();
     else if (a == "--seed") seed = std::stoull(val());
     else if (a == "--device") device = std::stoi(val());
+    else if (a == "--gpus") gpus = (uint32_t)std::stoul(val());
     else if (a == "--lib") lib = val();
     else if (a == "--out-dir") out_dir = val();
     else if (a == "--progress-out") progress_out = val();
@@ -170,11 +173,12 @@ int main(int argc, char** argv) {
             b = rtwh::to_vec_cobs(m);
             fwrite(b.data(), 1, b.size(), progress);
           }
-          fprintf(stderr, "frame %u: %ux%u, %u spp, %llu segments, GPU render %.1f ms (%.1f Mrays/s) -> %s%s\n", frame_no,
-                  image_width, image_height, spp, (unsigned long long)st.segments, st.ms_render,
+          fprintf(stderr, "frame %u: %ux%u, %u spp, %llu segments, %u GPU(s), render %.1f ms (%.1f Mrays/s) -> %s%s\n", frame_no,
+                  image_width, image_height, spp, (unsigned long long)st.segments, st.gpus, st.ms_render,
                   st.ms_render > 0 ? st.segments / (st.ms_render * 1e3) : 0.0, out_dir.c_str(), name);
           return true;
-        });
+        },
+        gpus);
     double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (progress) fclose(progress);
     rtwh_sink_close(&sink);

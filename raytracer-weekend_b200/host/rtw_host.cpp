@@ -377,7 +377,7 @@ int anim_trampoline(void* user, uint32_t frame, const float* accum, const rtw_re
 }  // namespace
 
 uint32_t render_animation(const World& world, uint32_t w, uint32_t h, uint32_t spp, rtw_sink* sink, uint64_t seed,
-                          const FrameFn& on_frame) {
+                          const FrameFn& on_frame, uint32_t gpus) {
   flatten_world(world.objects, sink);
   rtw_render_params p;
   memset(&p, 0, sizeof(p));
@@ -387,6 +387,7 @@ uint32_t render_animation(const World& world, uint32_t w, uint32_t h, uint32_t s
   p.max_depth = 50;  // MAX_DEPTH (lib.rs:32)
   p.background[0] = world.background.x(); p.background[1] = world.background.y(); p.background[2] = world.background.z();
   p.seed = seed;
+  p.gpus = gpus;
   std::vector<rtw_camera> cams;
   for (const auto& c : world.cameras) cams.push_back(c.c);
   AnimCtx ctx{&on_frame, w, h, {}};

@@ -390,8 +390,9 @@ std::vector<Pixel> pixels_from_accum(const float* accum_rgb, uint32_t w, uint32_
 // once): frame i = cameras[i], stream seed + i.  on_frame(frame_no, pixels, stats) runs on a helper thread while
 // the next frame renders; returning false stops the animation.  Returns the number of frames delivered.
 using FrameFn = std::function<bool(uint32_t, const std::vector<Pixel>&, const rtw_render_stats&)>;
+// gpus > 1: every frame is spread over that many devices of the box (rtw_render_params::gpus) — same bits.
 uint32_t render_animation(const World& world, uint32_t image_width, uint32_t image_height, uint32_t samples_per_pixel,
-                          rtw_sink* sink, uint64_t seed, const FrameFn& on_frame);
+                          rtw_sink* sink, uint64_t seed, const FrameFn& on_frame, uint32_t gpus = 1);
 
 // flatten a whole world (top-level list order = canonical order) and build it
 void flatten_world(const HittableList& world, rtw_sink* sink, float time0 = 0.f, float time1 = 1.f,
