@@ -637,6 +637,9 @@ int build_scene_device(rtw_scene* s, float time0, float time1, rtw_build_stats* 
         m.r = s->textures[m.tex].f0; m.g = s->textures[m.tex].f1; m.b = s->textures[m.tex].f2;
       }
     }
+    d.all_diffuse_solid = 1;
+    for (const MaterialRec& m : mats)
+      if (!((m.type == MT_LAMBERTIAN || m.type == MT_DIFFUSE_LIGHT) && m.solid)) d.all_diffuse_solid = 0;
     if ((rc = dev_upload(s, &d.materials, mats))) return rc;
   }
   if ((rc = dev_upload(s, &d.textures, s->textures))) return rc;

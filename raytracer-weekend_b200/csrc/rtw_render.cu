@@ -147,7 +147,7 @@ struct WaveHost {
   cudaGraphExec_t graph_exec = nullptr;
   int blocks_trav[TK_N] = {};      // persistent grid per TravKind
   int blocks_shade = 0;
-  int blocks_mega = 0;
+  int blocks_mega[2] = {0, 0};  // [LEAN]
 };
 
 // ---- work items ---------------------------------------------------------------------------------
@@ -236,10 +236,8 @@ __device__ __forceinline__ bool fetch_item(const FrameDev& f, WaveCtl* ctl, bool
 
 // lib.rs:84-86: the camera ray of sample `it.sample` of the item's pixel (stage 0 of the path's stream).
 __device__ __forceinline__ void camera_path(const FrameDev& f, const Item& it, v3& o, v3& d, float& time) {
-  Rng rng;
-  rng.begin(((uint64_t)f.seed_hi << 32) | f.seed_lo, it.pixel, it.sample, 0);
-  uint32_t row = it.pixel / f.width, col = it.pixel % f.width;
-  camera_ray(f.cam, f.width, f.height, row, col, rng, o, d, time);
+  uint32_t row = it.pixel / f.width, col = it.pixel - row * f.width;
+  camera_ray_fresh(f.cam, f.width, f.height, row, col, ((uint64_t)f.seed_hi << 32) | f.seed_lo, it.pixel, it.sample, o, d, time);
 }
 
 __device__ __forceinline__ void start_path(const FrameDev& f, const WaveDev& w, uint32_t slot, const Item& it) {
@@ -268,21 +266,34 @@ __device__ __forceinline__ void publish_item(const FrameDev& f, float4* __restri
 // geometry words g0..g2 at distance t.  Returns true when the path ENDS with this segment (L = the radiance it
 // contributes, throughput applied); otherwise T, bounce and the ray are advanced to the scattered ray.
 // Shared by the wavefront shade kernel and the fused flat-scene kernel: one copy of the parity-critical arithmetic.
-template <class IV>
+// LEAN: the scene's materials are all Lambertian / DiffuseLight over solid colours (SceneDev::all_diffuse_solid): the
+// metal / glass / texture code is compiled out (fewer registers, a third of the code).
+template <bool LEAN = false, class IV>
 __device__ __forceinline__ bool shade_hit(const SceneDev& sc, const IV& iv, uint32_t max_depth, uint32_t meta,
                                           const MaterialRec& m, int32_t shade_idx, float4 g0, float4 g1, float4 g2, float t,
                                           uint64_t seed, uint32_t pixel, uint32_t sample, v3& o, v3& d, float time, v3& T,
                                           uint32_t& bounce, v3& L) {
-  const bool need_uv = !m.solid && (m.type == MT_LAMBERTIAN || m.type == MT_DIFFUSE_LIGHT) && texture_needs_uv(sc, m.tex);
+  const bool need_uv = !LEAN && !m.solid && (m.type == MT_LAMBERTIAN || m.type == MT_DIFFUSE_LIGHT) && texture_needs_uv(sc, m.tex);
   HitRec rec;
   finalize_hit_iv(sc, iv, meta & 7u, meta >> RTW_META_TYPE_BITS, g0, g1, g2, shade_idx, o, d, time, t, need_uv, rec);
-  const v3 emitted = material_emitted(sc, m, rec);  // lib.rs:107-109
   Rng rng;
   rng.begin(seed, pixel, sample, bounce + 1);
   v3 att, out_dir;
-  if (!material_scatter(sc, m, d, rec, rng, att, out_dir)) {  // lib.rs:111-114
-    L = T * emitted;
-    return true;
+  if (LEAN) {
+    if (m.type != MT_LAMBERTIAN) {  // DiffuseLight: emits its solid colour, never scatters (light_source.rs:17-23)
+      L = T * mk(m.r, m.g, m.b);
+      return true;
+    }
+    out_dir = rec.normal + unit_vector(random_in_unit_sphere_fresh(rng));  // material.rs:42-56, as in material_scatter
+    const float S = 1e-8f;
+    if ((fabsf(out_dir.x) < S) && (fabsf(out_dir.y) < S) && (fabsf(out_dir.z) < S)) out_dir = rec.normal;
+    att = mk(m.r, m.g, m.b);
+  } else {
+    const v3 emitted = material_emitted(sc, m, rec);  // lib.rs:107-109
+    if (!material_scatter(sc, m, d, rec, rng, att, out_dir)) {  // lib.rs:111-114
+      L = T * emitted;
+      return true;
+    }
   }
   // L += T*emitted with emitted == 0 for every scattering material: exact no-op
   T = T * att;  // lib.rs:116
@@ -597,7 +608,7 @@ __global__ void __launch_bounds__(128) k_wave_shade(
 // A lane whose path ended restarts at the top of the next trip (all lanes of a warp run the list walk together again);
 // a warp leaves when the cursor is dry and none of its lanes holds a path.
 #ifndef RTW_MEGA_MINBLOCKS
-#define RTW_MEGA_MINBLOCKS 4
+#define RTW_MEGA_MINBLOCKS 6  // r02 A/B (Cornell, Mrays/s): 4 -> 10318, 5 -> 10326, 6 -> 10950 (80 registers, 24 warps per SM)
 #endif
 #define RTW_MEGA_MAX_OPS 264  // 33 chains x RTW_MAX_CHAIN
 
@@ -609,6 +620,10 @@ struct MegaShared {
   InstOp inst_ops[RTW_MEGA_MAX_OPS];
 };
 
+#ifndef RTW_MEGA_REGEN_MIN
+#define RTW_MEGA_REGEN_MIN 4  // r02 A/B: 1 -> 10318, 4 -> 10737, 8 -> 10620 Mrays/s. lanes that must be waiting before a warp runs the restart code (or no lane holds a path)
+#endif
+template <bool LEAN>
 __global__ void __launch_bounds__(128, RTW_MEGA_MINBLOCKS) k_mega_flat(SceneDev sc, FrameDev f, float4* __restrict__ partial,
                                                                       WaveCtl* __restrict__ ctl) {
   __shared__ MegaShared sh;
@@ -621,7 +636,6 @@ __global__ void __launch_bounds__(128, RTW_MEGA_MINBLOCKS) k_mega_flat(SceneDev 
   for (uint32_t i = threadIdx.x; i < sc.num_inst_ops; i += blockDim.x) sh.inst_ops[i] = sc.inst_ops[i];
   stage_flat(sc, sh.fr);  // ends with __syncthreads()
   const SharedInst iv{sh.inst_range, sh.inst_ops};
-  const uint32_t nprim = sc.flat_count;
   const uint32_t lane = threadIdx.x & 31;
   const uint64_t seed = ((uint64_t)f.seed_hi << 32) | f.seed_lo;
   uint32_t nseg = 0, npaths = 0;
@@ -637,7 +651,8 @@ __global__ void __launch_bounds__(128, RTW_MEGA_MINBLOCKS) k_mega_flat(SceneDev 
   for (;;) {
     // ---- (re)start paths: next sample of the lane's item, or a new item ---------------------------------------------
     const bool want = !have && !done;
-    if (__any_sync(0xffffffffu, want)) {
+    const uint32_t m_want = __ballot_sync(0xffffffffu, want);
+    if (m_want != 0u && ((uint32_t)__popc(m_want) >= RTW_MEGA_REGEN_MIN || !__any_sync(0xffffffffu, have))) {
       bool go = want && !need_item;
       Item nit = it;
       if (fetch_item(f, ctl, want && need_item, nit)) {
@@ -661,7 +676,7 @@ __global__ void __launch_bounds__(128, RTW_MEGA_MINBLOCKS) k_mega_flat(SceneDev 
     float best_t = __int_as_float(0x7f800000);
     int32_t best_slot;
     uint32_t best_meta;
-    flat_closest(iv, sh.fr, nprim, o, d, time, 0.001f, have, best_t, best_slot, best_meta);
+    flat_closest(iv, sh.fr, o, d, time, 0.001f, have, best_t, best_slot, best_meta);
     // ---- shade ---------------------------------------------------------------------------------------------------------
     if (have) {
       nseg++;
@@ -671,7 +686,7 @@ __global__ void __launch_bounds__(128, RTW_MEGA_MINBLOCKS) k_mega_flat(SceneDev 
         L = T * f.background;
         ended = true;
       } else {
-        ended = shade_hit(sc, iv, f.max_depth, best_meta, sh.mat[best_slot], sh.shade[best_slot], sh.fr.g[best_slot][0],
+        ended = shade_hit<LEAN>(sc, iv, f.max_depth, best_meta, sh.mat[best_slot], sh.shade[best_slot], sh.fr.g[best_slot][0],
                           sh.fr.g[best_slot][1], sh.fr.g[best_slot][2], best_t, seed, it.pixel, it.sample, o, d, time, T,
                           bounce, L);
       }
@@ -809,8 +824,10 @@ int create_wave(rtw_scene* s, WaveHost** out) {
   }
   RTW_WAVE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wave_shade, 128, 0));
   wh->blocks_shade = std::max(nb, 1) * s->num_sms;
-  RTW_WAVE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_mega_flat, 128, 0));
-  wh->blocks_mega = std::max(nb, 1) * s->num_sms;
+  RTW_WAVE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_mega_flat<false>, 128, 0));
+  wh->blocks_mega[0] = std::max(nb, 1) * s->num_sms;
+  RTW_WAVE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_mega_flat<true>, 128, 0));
+  wh->blocks_mega[1] = std::max(nb, 1) * s->num_sms;
 #undef RTW_WAVE_TRY
   *out = wh;
   return RTW_OK;
@@ -1004,9 +1021,12 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
   if (f.n_items > 0 && mega) {
     // ---- one-leaf scene: the whole frame is one launch ---------------------------------------------------------------
     const unsigned long long need_blocks = (f.n_items + 127ull) / 128ull;
-    int grid = (int)std::min<unsigned long long>((unsigned long long)wh->blocks_mega, std::max<unsigned long long>(need_blocks, 1ull));
+    bool lean = s->dev.all_diffuse_solid != 0;
+    if (const char* e = getenv("RTW_MEGA_LEAN")) lean = lean && atoi(e) != 0;  // 0: A/B against the full kernel
+    int grid = (int)std::min<unsigned long long>((unsigned long long)wh->blocks_mega[lean ? 1 : 0], std::max<unsigned long long>(need_blocks, 1ull));
     if (fault && !strcmp(fault, "launch")) grid = -1;
-    k_mega_flat<<<grid, 128, 0, st>>>(s->dev, f, wh->partial, wh->d_ctl);
+    if (lean) k_mega_flat<true><<<grid, 128, 0, st>>>(s->dev, f, wh->partial, wh->d_ctl);
+    else k_mega_flat<false><<<grid, 128, 0, st>>>(s->dev, f, wh->partial, wh->d_ctl);
     RTW_CUDA_TRY(cudaGetLastError());
     launches++;
     iterations = 1;

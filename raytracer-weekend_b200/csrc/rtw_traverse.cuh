@@ -476,13 +476,17 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
 
 // Flat scenes (SceneDev::flat_count > 0: at most 32 primitives in one leaf, e.g. the Cornell box): every ray tests
 // every primitive, in the same order — there is nothing to walk and nothing to balance.  The primitive records are
-// staged in shared memory once per block (48 B geometry + meta + canonical id), the loop over them is warp-uniform
-// (broadcast LDS, no per-lane addressing, uniform type / instance branches) and a warp simply takes 32 rays at a
-// time.  Same tests, same order of the float operations, same tie rule as traverse_persistent.
+// staged in shared memory once per block (48 B geometry + meta + canonical id) together with their RUNS: the build
+// sorted the slots of a leaf by (instance, type), so the list is a handful of runs of equal instance and type.  The
+// loop over runs is warp-uniform: the ray is transformed once per instance, the primitive type is dispatched once per
+// run, and inside a run of rectangles every test divides by the same direction component (SharedDivisor) and is
+// branch free.  Same tests, same order of the float operations, same tie rule as traverse_persistent.
 struct FlatRecords {
   float4 g[32][3];
   uint32_t meta[32];
   int32_t prim[32];
+  uint32_t run[32];  // first | count << 8 | type << 16 | instance << 19
+  uint32_t nruns;
 };
 
 __device__ __forceinline__ void stage_flat(const SceneDev& sc, FlatRecords& fr) {
@@ -491,58 +495,85 @@ __device__ __forceinline__ void stage_flat(const SceneDev& sc, FlatRecords& fr) 
     fr.meta[i] = sc.slot_meta[i];
     fr.prim[i] = sc.slot_prim[i];
   }
+  if (threadIdx.x == 0) {
+    uint32_t nruns = 0, first = 0;
+    for (uint32_t i = 1; i <= sc.flat_count; ++i) {
+      const uint32_t pm0 = sc.slot_meta[first];
+      if (i == sc.flat_count || sc.slot_meta[i] != pm0) {
+        fr.run[nruns++] = first | ((i - first) << 8) | ((pm0 & 7u) << 16) | ((pm0 >> RTW_META_TYPE_BITS) << 19);
+        first = i;
+      }
+    }
+    fr.nruns = nruns;
+  }
   __syncthreads();
 }
 
 // The closest hit of one ray over the staged records: every lane of the warp walks the list together (call with the
 // whole warp; `active` = this lane holds a ray).  best_t comes in as the ray's t_max.
 template <class IV>
-__device__ __forceinline__ void flat_closest(const IV& iv, const FlatRecords& fr, uint32_t nprim, v3 o, v3 d, float time,
-                                             float t_min, bool active, float& best_t, int32_t& best_slot,
-                                             uint32_t& best_meta) {
-  int32_t best_id = -2;
-  uint32_t cur_inst = 0;
+__device__ __forceinline__ void flat_closest(const IV& iv, const FlatRecords& fr, v3 o, v3 d, float time, float t_min,
+                                             bool active, float& best_t, int32_t& best_slot, uint32_t& best_meta) {
   best_slot = -1;
   best_meta = 0;
+  uint32_t cur_inst = 0;
   v3 oi = o, di = d;
-  for (uint32_t k = 0; k < nprim; ++k) {  // warp-uniform
-    const uint32_t pm = fr.meta[k];
-    const uint32_t type = pm & 7u, inst = pm >> RTW_META_TYPE_BITS;
+  // closest-so-far update with the list rule (hittable/mod.rs:57-69): a hit at t <= best_t replaces the record; among
+  // bit-equal t the later primitive of the CANONICAL order wins (the slots are not in canonical order)
+  auto accept = [&](bool hit, float t, uint32_t k) {
+    if (hit && active) {
+      const bool closer = best_slot < 0 || t < best_t;
+      if (closer || fr.prim[k] > fr.prim[best_slot]) {
+        best_t = closer ? t : best_t;
+        best_slot = (int32_t)k;
+      }
+    }
+  };
+  const uint32_t nruns = fr.nruns;
+  for (uint32_t r = 0; r < nruns; ++r) {  // warp-uniform
+    const uint32_t run = fr.run[r];
+    const uint32_t first = run & 0xffu, last = first + ((run >> 8) & 0xffu), type = (run >> 16) & 7u, inst = run >> 19;
     if (inst != cur_inst) {
       oi = o; di = d;
       if (inst != 0) ray_to_instance_iv(iv, inst, oi, di);
       cur_inst = inst;
     }
-    const float4 g0 = fr.g[k][0];
-    float t, a, b;
-    bool hit;
-    if (type == PT_RECT_XZ)
-      hit = rect_t_perm(oi.x, oi.z, oi.y, di.x, di.z, di.y, t_min, best_t, g0, fr.g[k][1].x, t);
-    else if (type == PT_RECT_XY)
-      hit = rect_t_perm(oi.x, oi.y, oi.z, di.x, di.y, di.z, t_min, best_t, g0, fr.g[k][1].x, t);
-    else if (type == PT_RECT_YZ)
-      hit = rect_t_perm(oi.y, oi.z, oi.x, di.y, di.z, di.x, t_min, best_t, g0, fr.g[k][1].x, t);
-    else if (type <= PT_MSPHERE) {
-      v3 center = mk(g0.x, g0.y, g0.z);
-      if (type == PT_MSPHERE) center = moving_center(g0, fr.g[k][1], fr.g[k][2], time);
-      hit = sphere_t(oi, di, t_min, best_t, center, g0.w, t);
+    if (type >= PT_RECT_YZ && type <= PT_RECT_XY) {
+      // permute once per run: (in-plane A, in-plane B, constant axis K) — rectangular.rs:27-57 / 78-108 / 129-159
+      float oA, oB, oK, dA, dB, dK;
+      if (type == PT_RECT_XZ) { oA = oi.x; oB = oi.z; oK = oi.y; dA = di.x; dB = di.z; dK = di.y; }
+      else if (type == PT_RECT_XY) { oA = oi.x; oB = oi.y; oK = oi.z; dA = di.x; dB = di.y; dK = di.z; }
+      else { oA = oi.y; oB = oi.z; oK = oi.x; dA = di.y; dB = di.z; dK = di.x; }
+      SharedDivisor dv;
+      dv.set(dK);
+      for (uint32_t k = first; k < last; ++k) {
+        float t;
+        const bool hit = rect_t_shared(dv, oA, oB, oK, dA, dB, t_min, best_t, fr.g[k][0], fr.g[k][1].x, t);
+        accept(hit, t, k);
+      }
+    } else if (type <= PT_MSPHERE) {
+      for (uint32_t k = first; k < last; ++k) {
+        const float4 g0 = fr.g[k][0];
+        v3 center = mk(g0.x, g0.y, g0.z);
+        if (type == PT_MSPHERE) center = moving_center(g0, fr.g[k][1], fr.g[k][2], time);
+        float t;
+        const bool hit = sphere_t(oi, di, t_min, best_t, center, g0.w, t);
+        accept(hit, t, k);
+      }
     } else {
-      hit = tri_t(oi, di, t_min, best_t, g0, fr.g[k][1], fr.g[k][2], t, a, b);
-    }
-    if (hit && active) {
-      if (best_slot < 0 || t < best_t) {
-        best_t = t; best_slot = (int32_t)k; best_meta = pm; best_id = fr.prim[k];
-      } else if (fr.prim[k] > best_id) {  // t == best_t: the later primitive of the canonical order wins
-        best_slot = (int32_t)k; best_meta = pm; best_id = fr.prim[k];
+      for (uint32_t k = first; k < last; ++k) {
+        float t, a, b;
+        const bool hit = tri_t(oi, di, t_min, best_t, fr.g[k][0], fr.g[k][1], fr.g[k][2], t, a, b);
+        accept(hit, t, k);
       }
     }
   }
+  if (best_slot >= 0) best_meta = fr.meta[best_slot];
 }
 
 template <class IO>
 __device__ __forceinline__ void traverse_flat(const SceneDev& sc, const FlatRecords& fr, IO& io, uint32_t count, uint32_t* cursor) {
   const uint32_t lane = threadIdx.x & 31;
-  const uint32_t nprim = sc.flat_count;
   const GlobalInst iv{sc.inst_range, sc.inst_ops};
   for (;;) {
     uint32_t base = 0;
@@ -557,7 +588,7 @@ __device__ __forceinline__ void traverse_flat(const SceneDev& sc, const FlatReco
     const bool active = index < count && io.load(index, o, d, time, t_min, best_t, slot0, resumed);
     int32_t best_slot;
     uint32_t best_meta;
-    flat_closest(iv, fr, nprim, o, d, time, t_min, active, best_t, best_slot, best_meta);
+    flat_closest(iv, fr, o, d, time, t_min, active, best_t, best_slot, best_meta);
     if (active) io.store(index, o, d, time, best_slot, best_t, best_meta);
   }
 }
