@@ -517,9 +517,11 @@ class Scene:
         p.background[0], p.background[1], p.background[2] = bg
         return p
 
-    def render(self, cam: Camera, params: RenderParams):
-        """rtw_render with HOST buffers: returns (accum[h, w, 3] float32, RenderStats)."""
-        accum = np.zeros((params.height, params.width, 3), np.float32)
+    def render(self, cam: Camera, params: RenderParams, out: Optional[np.ndarray] = None):
+        """rtw_render with HOST buffers: returns (accum[h, w, 3] float32, RenderStats).  `out`: an existing host frame
+        (C-contiguous float32 [h, w, 3]) to render into instead of a new array."""
+        accum = np.zeros((params.height, params.width, 3), np.float32) if out is None else out
+        assert accum.dtype == np.float32 and accum.flags.c_contiguous and accum.size == params.height * params.width * 3
         st = RenderStats()
         self._c("render", C.byref(cam), C.byref(params), accum.ctypes.data, C.byref(st))
         return accum, st

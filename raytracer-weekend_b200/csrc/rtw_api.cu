@@ -108,7 +108,6 @@ int rtw_scene_destroy(rtw_scene* s) {
     free_wave(s);
     free_scene_device(s);
     if (s->io_frame) cudaFree(s->io_frame);
-    if (s->io_pinned) cudaFreeHost(s->io_pinned);
   }
   delete s;
   return RTW_OK;
@@ -179,13 +178,10 @@ int rtw_add_texture_image(rtw_scene* s, const uint8_t* rgb8, uint32_t width, uin
   t.i0 = (int)s->texels.size();
   t.i1 = (int)width;
   t.i2 = (int)height;
-  size_t n = (size_t)width * height;
-  s->texels.reserve(s->texels.size() + n);
-  for (size_t i = 0; i < n; ++i) {
-    uchar4 px;
-    px.x = rgb8[3 * i]; px.y = rgb8[3 * i + 1]; px.z = rgb8[3 * i + 2]; px.w = 255;
-    s->texels.push_back(px);
-  }
+  const size_t n = (size_t)width * height, base = s->texels.size();
+  s->texels.resize(base + n);
+  uchar4* dst = s->texels.data() + base;
+  for (size_t i = 0; i < n; ++i) dst[i] = make_uchar4(rgb8[3 * i], rgb8[3 * i + 1], rgb8[3 * i + 2], 255);
   s->textures.push_back(t);
   return (int)s->textures.size() - 1;
 }
@@ -543,20 +539,15 @@ int rtw_render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_para
   return rc;
 }
 
-// the frame buffer on the scene's device and its pinned host staging: kept on the scene, grow only
+// the frame buffer on the scene's device: kept on the scene, grow only
 static int ensure_io(rtw_scene* s, size_t bytes) {
   if (s->io_bytes >= bytes) return RTW_OK;
   if (s->io_frame) cudaFree(s->io_frame);
-  if (s->io_pinned) cudaFreeHost(s->io_pinned);
   s->io_frame = nullptr;
-  s->io_pinned = nullptr;
   s->io_bytes = 0;
   cudaError_t e = cudaMalloc((void**)&s->io_frame, bytes);
-  if (e == cudaSuccess) e = cudaMallocHost((void**)&s->io_pinned, bytes);
   if (e != cudaSuccess) {
     cudaGetLastError();
-    if (s->io_frame) cudaFree(s->io_frame);
-    s->io_frame = nullptr;
     return set_error(RTW_ERR_NOMEM, std::string("render: frame buffer allocation failed: ") + cudaGetErrorString(e));
   }
   s->io_bytes = bytes;
@@ -575,10 +566,10 @@ int rtw_render(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* par
                         : render_device(s, cam, params, s->io_frame, 0, stats);
   if (rc != RTW_OK) return rc;
   if (stats && stats->gpus == 0) stats->gpus = 1;
-  // device -> pinned staging at link speed, then into the caller's (pageable) buffer
-  cudaError_t e = cudaMemcpy(s->io_pinned, s->io_frame, bytes, cudaMemcpyDeviceToHost);
+  // Straight into the caller's buffer.  (A pinned staging buffer of the frame's size costs more to allocate — 40 ms for
+  // a 4K frame — than the driver's own staged copy of a pageable destination takes; measured r02.)
+  cudaError_t e = cudaMemcpy(accum_rgb, s->io_frame, bytes, cudaMemcpyDeviceToHost);
   if (e != cudaSuccess) return cuda_fail(e, "rtw_render readback");
-  memcpy(accum_rgb, s->io_pinned, bytes);
   return RTW_OK;
 }
 

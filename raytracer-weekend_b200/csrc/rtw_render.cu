@@ -608,7 +608,7 @@ __global__ void __launch_bounds__(128) k_wave_shade(
 // A lane whose path ended restarts at the top of the next trip (all lanes of a warp run the list walk together again);
 // a warp leaves when the cursor is dry and none of its lanes holds a path.
 #ifndef RTW_MEGA_MINBLOCKS
-#define RTW_MEGA_MINBLOCKS 6  // r02 A/B (Cornell, Mrays/s): 4 -> 10318, 5 -> 10326, 6 -> 10950 (80 registers, 24 warps per SM)
+#define RTW_MEGA_MINBLOCKS 7  // r02 A/B (Cornell, final code): 5 -> 11256, 6 -> 12407, 7 -> 12942 Mrays/s (72 registers, 28 warps per SM)
 #endif
 #define RTW_MEGA_MAX_OPS 264  // 33 chains x RTW_MAX_CHAIN
 

@@ -64,9 +64,8 @@ struct rtw_scene {
 
   // render scratch kept between calls (rtw_render.cu)
   void* wave = nullptr;
-  // rtw_render (host buffers): frame buffer on the device + pinned staging, kept between calls (grow only)
+  // rtw_render (host buffers): frame buffer on the device, kept between calls (grow only)
   float* io_frame = nullptr;
-  float* io_pinned = nullptr;
   size_t io_bytes = 0;
   // multi-GPU (rtw_render_params::gpus > 1): replicas of this scene on the other devices, created on first use;
   // staging[i] = device memory of THIS scene's device for replica i's frame when peer stores are not possible

@@ -485,8 +485,9 @@ struct FlatRecords {
   float4 g[32][3];
   uint32_t meta[32];
   int32_t prim[32];
-  uint32_t run[32];  // first | count << 8 | type << 16 | instance << 19
+  uint4 run[32];     // first slot, one past the last, primitive type, instance
   uint32_t nruns;
+  uint32_t k_safe;   // every rectangle plane k passes plane_div_safe: a run may skip the per-numerator window test
 };
 
 __device__ __forceinline__ void stage_flat(const SceneDev& sc, FlatRecords& fr) {
@@ -496,17 +497,48 @@ __device__ __forceinline__ void stage_flat(const SceneDev& sc, FlatRecords& fr) 
     fr.prim[i] = sc.slot_prim[i];
   }
   if (threadIdx.x == 0) {
-    uint32_t nruns = 0, first = 0;
+    uint32_t nruns = 0, first = 0, k_safe = 1;
     for (uint32_t i = 1; i <= sc.flat_count; ++i) {
       const uint32_t pm0 = sc.slot_meta[first];
       if (i == sc.flat_count || sc.slot_meta[i] != pm0) {
-        fr.run[nruns++] = first | ((i - first) << 8) | ((pm0 & 7u) << 16) | ((pm0 >> RTW_META_TYPE_BITS) << 19);
+        fr.run[nruns++] = make_uint4(first, i, pm0 & 7u, pm0 >> RTW_META_TYPE_BITS);
         first = i;
       }
     }
+    for (uint32_t i = 0; i < sc.flat_count; ++i) {
+      const uint32_t type = sc.slot_meta[i] & 7u;
+      if (type >= PT_RECT_YZ && type <= PT_RECT_XY) {
+        const float k = sc.geom[3 * (size_t)i + 1].x;
+        if (!plane_div_safe(k)) k_safe = 0;
+      }
+    }
     fr.nruns = nruns;
+    fr.k_safe = k_safe;
   }
   __syncthreads();
+}
+
+// One run of rectangles of one orientation: (oA, oB, oK) / (dA, dB, dK) = the ray permuted to (in-plane A, in-plane B,
+// constant axis K) — rectangular.rs:27-57 / 78-108 / 129-159.  Every test divides by dK: one exact reciprocal for the
+// run when the operands allow it (SharedDivisor), the plain division otherwise.
+#ifndef RTW_FLAT_UNROLL
+#define RTW_FLAT_UNROLL 1  // the fused kernel's hot code must stay inside the 32 KB instruction cache (r02 A/B)
+#endif
+constexpr int kFlatUnroll = RTW_FLAT_UNROLL;
+template <class Accept>
+__device__ __forceinline__ void flat_rect_run(const FlatRecords& fr, uint32_t first, uint32_t last, float oA, float oB, float oK,
+                                              float dA, float dB, float dK, float t_min, const float& best_t, Accept&& accept) {
+  SharedDivisor dv;
+  dv.set(dK);
+  const bool run_fast = dv.fast && fr.k_safe && origin_div_safe(oK);  // true for every lane in practice
+#pragma unroll kFlatUnroll
+  for (uint32_t k = first; k < last; ++k) {
+    const float num = fr.g[k][1].x - oK;
+    float t;
+    if (run_fast) t = dv.div_in_window(num);
+    else t = div_exact(num, dK);
+    accept(rect_accept(t, oA, oB, dA, dB, t_min, best_t, fr.g[k][0]), t, k);
+  }
 }
 
 // The closest hit of one ray over the staged records: every lane of the warp walks the list together (call with the
@@ -516,53 +548,47 @@ __device__ __forceinline__ void flat_closest(const IV& iv, const FlatRecords& fr
                                              bool active, float& best_t, int32_t& best_slot, uint32_t& best_meta) {
   best_slot = -1;
   best_meta = 0;
+  int32_t best_prim = -1;
   uint32_t cur_inst = 0;
   v3 oi = o, di = d;
-  // closest-so-far update with the list rule (hittable/mod.rs:57-69): a hit at t <= best_t replaces the record; among
-  // bit-equal t the later primitive of the CANONICAL order wins (the slots are not in canonical order)
+  // closest-so-far update with the list rule (hittable/mod.rs:57-69), branch free: a hit at t <= best_t replaces the
+  // record; among bit-equal t the later primitive of the CANONICAL order wins (the slots are not in canonical order)
   auto accept = [&](bool hit, float t, uint32_t k) {
-    if (hit && active) {
-      const bool closer = best_slot < 0 || t < best_t;
-      if (closer || fr.prim[k] > fr.prim[best_slot]) {
-        best_t = closer ? t : best_t;
-        best_slot = (int32_t)k;
-      }
-    }
+    const int32_t prim_k = fr.prim[k];
+    const bool h = hit && active;
+    const bool closer = h && (best_slot < 0 || t < best_t);
+    const bool take = closer || (h && prim_k > best_prim);
+    best_t = closer ? t : best_t;
+    best_slot = take ? (int32_t)k : best_slot;
+    best_prim = take ? prim_k : best_prim;
   };
   const uint32_t nruns = fr.nruns;
   for (uint32_t r = 0; r < nruns; ++r) {  // warp-uniform
-    const uint32_t run = fr.run[r];
-    const uint32_t first = run & 0xffu, last = first + ((run >> 8) & 0xffu), type = (run >> 16) & 7u, inst = run >> 19;
+    const uint4 run = fr.run[r];
+    const uint32_t first = run.x, last = run.y, type = run.z, inst = run.w;
     if (inst != cur_inst) {
       oi = o; di = d;
       if (inst != 0) ray_to_instance_iv(iv, inst, oi, di);
       cur_inst = inst;
     }
-    if (type >= PT_RECT_YZ && type <= PT_RECT_XY) {
-      // permute once per run: (in-plane A, in-plane B, constant axis K) — rectangular.rs:27-57 / 78-108 / 129-159
-      float oA, oB, oK, dA, dB, dK;
-      if (type == PT_RECT_XZ) { oA = oi.x; oB = oi.z; oK = oi.y; dA = di.x; dB = di.z; dK = di.y; }
-      else if (type == PT_RECT_XY) { oA = oi.x; oB = oi.y; oK = oi.z; dA = di.x; dB = di.y; dK = di.z; }
-      else { oA = oi.y; oB = oi.z; oK = oi.x; dA = di.y; dB = di.z; dK = di.x; }
-      SharedDivisor dv;
-      dv.set(dK);
-      for (uint32_t k = first; k < last; ++k) {
-        float t;
-        const bool hit = rect_t_shared(dv, oA, oB, oK, dA, dB, t_min, best_t, fr.g[k][0], fr.g[k][1].x, t);
-        accept(hit, t, k);
-      }
+    if (type == PT_RECT_XZ) {
+      flat_rect_run(fr, first, last, oi.x, oi.z, oi.y, di.x, di.z, di.y, t_min, best_t, accept);
+    } else if (type == PT_RECT_XY) {
+      flat_rect_run(fr, first, last, oi.x, oi.y, oi.z, di.x, di.y, di.z, t_min, best_t, accept);
+    } else if (type == PT_RECT_YZ) {
+      flat_rect_run(fr, first, last, oi.y, oi.z, oi.x, di.y, di.z, di.x, t_min, best_t, accept);
     } else if (type <= PT_MSPHERE) {
       for (uint32_t k = first; k < last; ++k) {
         const float4 g0 = fr.g[k][0];
         v3 center = mk(g0.x, g0.y, g0.z);
         if (type == PT_MSPHERE) center = moving_center(g0, fr.g[k][1], fr.g[k][2], time);
-        float t;
+        float t = 0.f;
         const bool hit = sphere_t(oi, di, t_min, best_t, center, g0.w, t);
         accept(hit, t, k);
       }
     } else {
       for (uint32_t k = first; k < last; ++k) {
-        float t, a, b;
+        float t = 0.f, a, b;
         const bool hit = tri_t(oi, di, t_min, best_t, fr.g[k][0], fr.g[k][1], fr.g[k][2], t, a, b);
         accept(hit, t, k);
       }
