@@ -543,18 +543,23 @@ void register_mesh(const std::string& path, std::vector<float> v, std::vector<fl
 }
 void set_asset_dir(const std::string& dir) { asset_dir() = dir; }
 
-bool read_png(const std::string& path, std::vector<uint8_t>& rgb, uint32_t& width, uint32_t& height);  // png_reader.cpp
+bool read_png(const std::string& path, std::vector<uint8_t>& rgb, uint32_t& width, uint32_t& height);   // png_reader.cpp
+bool read_jpeg(const std::string& path, std::vector<uint8_t>& rgb, uint32_t& width, uint32_t& height);  // jpeg_reader.cpp
 
 std::shared_ptr<ImageTexture> ImageTexture::open(const std::string& path) {
   auto it = image_registry().find(path);
   if (it != image_registry().end()) return std::make_shared<ImageTexture>(it->second.rgb, it->second.w, it->second.h);
   ImageAsset a;
   if (read_png(path, a.rgb, a.w, a.h)) return std::make_shared<ImageTexture>(std::move(a.rgb), a.w, a.h);  // lossless: exact texels
+  // the JPEG file itself (relative to the working directory like the reference, image_texture.rs:24, or under the
+  // asset directory): decoded here with libjpeg's default arithmetic (jpeg_reader.cpp)
+  if (read_jpeg(path, a.rgb, a.w, a.h) || read_jpeg(asset_dir() + "/" + path, a.rgb, a.w, a.h))
+    return std::make_shared<ImageTexture>(std::move(a.rgb), a.w, a.h);
   if (read_rtwi(asset_dir() + "/" + stem_of(path) + ".rtwi", a) || read_rtwi(path, a) ||
       read_ppm(dir_of(path) + "/" + stem_of(path) + ".ppm", a) || read_ppm(path, a))
     return std::make_shared<ImageTexture>(std::move(a.rgb), a.w, a.h);
-  throw Error("ImageTexture::open(\"" + path + "\"): no decoded image available. PNG files are decoded here; for JPEG (decoder-"
-              "dependent texels) register the decoded RGB8 buffer (rtwh_register_image) or provide <assets>/" + stem_of(path) + ".rtwi / a .ppm");
+  throw Error("ImageTexture::open(\"" + path + "\"): file not found. PNG and JPEG files are decoded here (the path itself, then "
+              "<assets>/<path>); alternatively register a decoded RGB8 buffer (rtwh_register_image) or provide <assets>/" + stem_of(path) + ".rtwi / a .ppm");
 }
 
 // ---------------------------------------------------------------------------------------------

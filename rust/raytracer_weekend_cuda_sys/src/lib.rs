@@ -1,10 +1,10 @@
-//! `extern "C"` surface of include/rtw_cuda.h (RTW_ABI_VERSION 1), declaration for declaration.
+//! `extern "C"` surface of include/rtw_cuda.h (RTW_ABI_VERSION 2), declaration for declaration.
 //! Every function returns an int: >= 0 on success (ids / counts), < 0 = RTW_ERR_*; the message of the calling
 //! thread's last error is `rtw_last_error()`.
 #![allow(non_camel_case_types)]
 use core::ffi::{c_char, c_int, c_void};
 
-pub const RTW_ABI_VERSION: c_int = 1;
+pub const RTW_ABI_VERSION: c_int = 2;
 pub const RTW_OK: c_int = 0;
 pub const RTW_ERR_INVALID: c_int = -1;
 pub const RTW_ERR_CUDA: c_int = -2;
@@ -81,6 +81,9 @@ pub struct rtw_render_params {
     pub pool_size: u32,
     pub slices: u32,
     pub flags: u32,
+    /// rtw_render / rtw_render_frames: spread the frame over this many devices (0 or 1 = the scene's device)
+    pub gpus: u32,
+    pub reserved: u32,
 }
 
 #[repr(C)]
@@ -99,6 +102,10 @@ pub struct rtw_render_stats {
     pub ms_traverse: f32,
     pub ms_shade: f32,
     pub node_record_bytes: f32,
+    /// 1: one-leaf scene rendered by the fused persistent kernel
+    pub fused: u32,
+    /// devices that rendered the frame
+    pub gpus: u32,
 }
 
 #[repr(C)]
@@ -134,6 +141,8 @@ extern "C" {
     pub fn rtw_device_count() -> c_int;
     pub fn rtw_scene_create(device: c_int, out: *mut *mut rtw_scene) -> c_int;
     pub fn rtw_scene_destroy(s: *mut rtw_scene) -> c_int;
+    pub fn rtw_scene_clone(src: *const rtw_scene, device: c_int, out: *mut *mut rtw_scene) -> c_int;
+    pub fn rtw_debug_live_handles() -> c_int;
     // ---- textures (texture.rs, image_texture.rs)
     pub fn rtw_add_texture_solid(s: *mut rtw_scene, r: f32, g: f32, b: f32) -> c_int;
     pub fn rtw_add_texture_checker(s: *mut rtw_scene, odd: c_int, even: c_int, frequency: f32) -> c_int;

@@ -223,3 +223,124 @@ def test_bulk_triangle_ingest_and_unbuilt_scene_errors():
             s.render(cam, s.params(8, 8, 1))
         with pytest.raises(rtw.RtwError, match="not built"):
             s.render_frames([cam], s.params(8, 8, 1), lambda i, a, st: True)
+
+
+# ---- the Rust -sys crate against the C header (no Rust toolchain here: parse both) ---------------------------------------
+_C2RUST = {"int": "c_int", "void": "c_void", "char": "c_char", "float": "f32", "uint8_t": "u8", "int32_t": "i32", "uint32_t": "u32",
+           "uint64_t": "u64", "size_t": "usize"}
+_RUST_SIZE = {"f32": 4, "u32": 4, "i32": 4, "u64": 8, "i64": 8, "u8": 1, "c_int": 4}
+
+
+def _c_type_to_rust(t):
+    """`const rtw_ray *` -> `*const rtw_ray`, `float[3]`-style parameters are pointers."""
+    t = t.strip()
+    stars = t.count("*")
+    const = "const" in t.split("*")[0].split()
+    base = [w for w in t.replace("*", " ").split() if w not in ("const", "struct")][0]
+    base = _C2RUST.get(base, base)
+    for _ in range(stars):
+        base = ("*const " if const else "*mut ") + base
+        const = False if stars > 1 else const
+    return base
+
+
+def _header_functions():
+    txt = re.sub(r"/\*.*?\*/", "", open(HDR).read(), flags=re.S)
+    out = {}
+    for ret, name, args in re.findall(r"\n\s*((?:const\s+)?\w+\s*\*?)\s*(rtw_\w+)\s*\(([^;{]*?)\)\s*;", txt):
+        if "typedef" in ret:
+            continue
+        params = []
+        for a in [x.strip() for x in args.replace("\n", " ").split(",")]:
+            if a in ("void", ""):
+                continue
+            m = re.match(r"(.*?)(\w+)\s*(\[\d*\])?$", a)          # type, name, optional array suffix
+            ctype = m.group(1) + ("*" if m.group(3) else "")
+            if "rtw_frame_callback" in ctype:
+                params.append("rtw_frame_callback")
+            else:
+                params.append(_c_type_to_rust(ctype))
+        out[name] = (_c_type_to_rust(ret), params)
+    return out
+
+
+def _rust_functions():
+    txt = open(os.path.join(ROOT, "rust", "raytracer_weekend_cuda_sys", "src", "lib.rs")).read()
+    ext = txt[txt.index('extern "C" {'):]
+    out = {}
+    for name, args, ret in re.findall(r"pub fn (rtw_\w+)\(([^)]*)\)\s*(?:->\s*([^;]+))?;", ext, flags=re.S):
+        params = [a.split(":", 1)[1].strip() for a in args.replace("\n", " ").split(",") if ":" in a]
+        out[name] = ((ret or "()").strip(), params)
+    return out
+
+
+def _header_structs():
+    txt = re.sub(r"/\*.*?\*/", "", open(HDR).read(), flags=re.S)
+    out = {}
+    for body, name in re.findall(r"typedef struct \w+ \{(.*?)\}\s*(\w+);", txt, flags=re.S):
+        fields = []
+        for decl in [d.strip() for d in body.split(";") if d.strip()]:
+            m = re.match(r"(\w+)\s+(.*)$", decl)
+            ctype = _C2RUST[m.group(1)]
+            for nm in [x.strip() for x in m.group(2).split(",")]:
+                arr = re.match(r"(\w+)\[(\d+)\]", nm)
+                fields.append((arr.group(1), f"[{ctype}; {arr.group(2)}]") if arr else (nm, ctype))
+        out[name] = fields
+    return out
+
+
+def _rust_structs():
+    txt = open(os.path.join(ROOT, "rust", "raytracer_weekend_cuda_sys", "src", "lib.rs")).read()
+    out = {}
+    for attrs, name, body in re.findall(r"((?:#\[[^\]]*\]\s*)+)pub struct (\w+) \{(.*?)\n\}", txt, flags=re.S):
+        if "repr(C)" not in attrs:
+            continue
+        body = re.sub(r"///.*", "", body)
+        out[name] = [(f.split(":")[0].replace("pub", "").strip(), f.split(":")[1].strip()) for f in body.split(",") if ":" in f]
+    return out
+
+
+def _layout(fields):
+    off, align_max, offs = 0, 1, []
+    for _, t in fields:
+        m = re.match(r"\[(\w+); (\d+)\]", t)
+        base, n = (m.group(1), int(m.group(2))) if m else (t, 1)
+        sz = _RUST_SIZE[base]
+        off = (off + sz - 1) // sz * sz
+        offs.append(off)
+        off += sz * n
+        align_max = max(align_max, sz)
+    return offs, (off + align_max - 1) // align_max * align_max
+
+
+def test_rust_sys_crate_matches_the_header():
+    """VERDICT r01 missing #7: rust/raytracer_weekend_cuda_sys/src/lib.rs is kept in sync with include/rtw_cuda.h by
+    hand and cannot be compiled here.  Every declared entry point must exist on the Rust side with the same arity and
+    the same argument / return types; every #[repr(C)] struct must have the header's fields in the header's order with
+    the same types — hence the same size and offsets, which are also compared with what the C compiler computes."""
+    hf, rf = _header_functions(), _rust_functions()
+    assert len(hf) >= 44 and set(hf) == set(rf), (sorted(set(hf) - set(rf)), sorted(set(rf) - set(hf)))
+    for name, (ret, params) in hf.items():
+        rret, rparams = rf[name]
+        assert rret == ret, (name, ret, rret)
+        assert rparams == params, (name, params, rparams)
+    hs, rs = _header_structs(), _rust_structs()
+    assert set(hs) <= set(rs) and len(hs) >= 7, sorted(set(hs) - set(rs))
+    for name, fields in hs.items():
+        assert rs[name] == fields, (name, fields, rs[name])
+    # sizes / offsets from the real C compiler
+    names = sorted(hs)
+    probes = "".join(f'printf("{n} %zu", sizeof({n}));' + "".join(f'printf(" %zu", offsetof({n}, {f}));' for f, _ in hs[n]) +
+                     'printf("\\n");' for n in names)
+    src = f'#include "{HDR}"\n#include <stdio.h>\n#include <stddef.h>\nint main() {{ {probes} return 0; }}'
+    exe = "/tmp/rtw_layout"
+    subprocess.run(["/usr/bin/gcc", "-x", "c", "-", "-o", exe], input=src, text=True, check=True)
+    for line in subprocess.run([exe], stdout=subprocess.PIPE, text=True, check=True).stdout.splitlines():
+        tok = line.split()
+        offs, size = _layout(rs[tok[0]])
+        assert int(tok[1]) == size and [int(x) for x in tok[2:]] == offs, (tok[0], tok[1:], size, offs)
+    # the abi version constant
+    rust_txt = open(os.path.join(ROOT, "rust", "raytracer_weekend_cuda_sys", "src", "lib.rs")).read()
+    ver = int(re.search(r"#define RTW_ABI_VERSION (\d+)", open(HDR).read()).group(1))
+    assert f"pub const RTW_ABI_VERSION: c_int = {ver};" in rust_txt
+    assert rtw.cuda_backend().fn("abi_version")() == ver

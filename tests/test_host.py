@@ -46,7 +46,7 @@ def test_jumpy_balls_is_seeded_and_faithful(oracle):
 def test_unsupported_scenes_fail_with_a_reason(oracle):
     with pytest.raises(rtw.RtwError, match="usemtl without mtllib"):
         rtw.Scene.from_name(oracle, "wavefront-suspension-obj", 1.0)
-    with pytest.raises(rtw.RtwError, match="no decoded image"):   # the PNG is missing from the reference tree too (.MISSING_LARGE_BLOBS)
+    with pytest.raises(rtw.RtwError, match="file not found"):   # the PNG is missing from the reference tree too (.MISSING_LARGE_BLOBS)
         rtw.Scene.from_name(oracle, "textured-monument", 1.0)
     with pytest.raises(rtw.RtwError, match="unknown scene"):
         rtw.Scene.from_name(oracle, "nope", 1.0)
@@ -393,7 +393,7 @@ def test_png_decoder_refuses_what_it_cannot_reproduce(tmp_path):
     Image.fromarray(np.arange(64, dtype=np.uint16).reshape(8, 8) * 900).save(tmp_path / "g16.png")      # 16-bit grey
     with pytest.raises(rtw.RtwError, match="bit depth 16"):
         rtw.open_image(str(tmp_path / "g16.png"))
-    with pytest.raises(rtw.RtwError, match="no decoded image"):              # JPEG stays a pre-decoded asset
+    with pytest.raises(rtw.RtwError, match="file not found"):              # JPEG stays a pre-decoded asset
         rtw.open_image(str(tmp_path / "nothing.jpg"))
 
 
@@ -431,3 +431,56 @@ def test_world_generated_once_flattens_like_from_name(oracle):
             assert np.array_equal(ha["material_id"], hc["material_id"]) and np.array_equal(bits(ha["normal"]), bits(hc["normal"]))
     with pytest.raises(rtw.RtwError, match="unknown scene"):
         rtw.World("nope", 1.0)
+
+
+# ---- JPEG ingest (image_texture.rs:23-30; host/jpeg_reader.cpp) ---------------------------------------------------------
+def test_jpeg_decoder_reproduces_the_committed_earthmap_fixture():
+    """VERDICT r01 missing #6: ImageTexture::open("models/earthmap.jpg") from the FILE.  The decoder follows libjpeg's
+    default arithmetic (islow IDCT, fixed-point YCbCr -> RGB), so its texels equal the committed PIL-decoded fixture
+    assets/earthmap.rtwi bit for bit — the stated +-1 LSB decoder caveat only concerns zune-jpeg."""
+    import os
+    jpg = os.path.join(rtw.ASSET_DIR, "models", "earthmap.jpg")
+    got = rtw.open_image(jpg)
+    want = rtw.read_rtwi(os.path.join(rtw.ASSET_DIR, "earthmap.rtwi"))
+    assert got.shape == (512, 1024, 3) and np.array_equal(got, want)
+    from PIL import Image
+    assert np.array_equal(got, np.asarray(Image.open(jpg).convert("RGB")))
+    # the scenes' own path resolves to the JPEG file under the asset directory
+    assert np.array_equal(rtw.open_image("models/earthmap.jpg"), want)
+
+
+def test_jpeg_decoder_against_pil_on_synthetic_files(tmp_path):
+    """baseline and progressive, 4:4:4 / 4:2:2 / 4:2:0 (libjpeg's fancy upsampling), restart markers, optimised Huffman
+    tables, grey, sizes that are not multiples of the MCU: every texel equal to PIL's (libjpeg-turbo)."""
+    from PIL import Image
+    rs = np.random.RandomState(0)
+
+    def img(w, h):
+        y, x = np.mgrid[0:h, 0:w]
+        base = np.stack([128 + 100 * np.sin(x / 7.0) * np.cos(y / 9.0), 128 + 90 * np.cos(x / 5.0 + y / 11.0), (x * 3 + y * 5) % 256], -1)
+        return np.clip(base + rs.normal(0, 12, (h, w, 3)), 0, 255).astype(np.uint8)
+
+    path = str(tmp_path / "t.jpg")
+    cases = 0
+    for (w, h) in [(64, 48), (37, 29), (1, 1), (17, 8), (200, 133)]:
+        for kw in [dict(quality=90, subsampling=0), dict(quality=75, subsampling=1), dict(quality=60, subsampling=2),
+                   dict(quality=85, subsampling=2, progressive=True), dict(quality=95, subsampling=0, progressive=True),
+                   dict(quality=80, subsampling=2, restart_marker_blocks=3), dict(quality=50, subsampling=0, optimize=True)]:
+            Image.fromarray(img(w, h)).save(path, "JPEG", **kw)
+            assert np.array_equal(rtw.open_image(path), np.asarray(Image.open(path).convert("RGB"))), (w, h, kw)
+            cases += 1
+        Image.fromarray(img(w, h)[..., 0]).save(path, "JPEG", quality=80)
+        assert np.array_equal(rtw.open_image(path), np.asarray(Image.open(path).convert("RGB"))), ("grey", w, h)
+    assert cases == 35
+
+
+def test_jpeg_decoder_errors(tmp_path):
+    p = tmp_path / "bad.jpg"
+    p.write_bytes(b"\xff\xd8\xff\xc9\x00\x0b\x08\x00\x10\x00\x10\x01\x01\x11\x00")      # SOF9: arithmetic coding
+    with pytest.raises(rtw.RtwError, match="unsupported coding process"):
+        rtw.open_image(str(p))
+    p.write_bytes(b"\xff\xd8\xff\xd9")
+    with pytest.raises(rtw.RtwError, match="no image data"):
+        rtw.open_image(str(p))
+    with pytest.raises(rtw.RtwError, match="not found"):
+        rtw.open_image(str(tmp_path / "missing.jpg"))
