@@ -46,7 +46,7 @@ def test_jumpy_balls_is_seeded_and_faithful(oracle):
 def test_unsupported_scenes_fail_with_a_reason(oracle):
     with pytest.raises(rtw.RtwError, match="usemtl without mtllib"):
         rtw.Scene.from_name(oracle, "wavefront-suspension-obj", 1.0)
-    with pytest.raises(rtw.RtwError, match="file not found"):   # the PNG is missing from the reference tree too (.MISSING_LARGE_BLOBS)
+    with pytest.raises(rtw.RtwError, match="no decoded image"):   # the PNG is missing from the reference tree too (.MISSING_LARGE_BLOBS)
         rtw.Scene.from_name(oracle, "textured-monument", 1.0)
     with pytest.raises(rtw.RtwError, match="unknown scene"):
         rtw.Scene.from_name(oracle, "nope", 1.0)
