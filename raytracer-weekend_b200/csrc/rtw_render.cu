@@ -289,8 +289,8 @@ __device__ __forceinline__ bool shade_hit(const SceneDev& sc, const IV& iv, uint
     if ((fabsf(out_dir.x) < S) && (fabsf(out_dir.y) < S) && (fabsf(out_dir.z) < S)) out_dir = rec.normal;
     att = mk(m.r, m.g, m.b);
   } else {
-    const v3 emitted = material_emitted(sc, m, rec);  // lib.rs:107-109
-    if (!material_scatter(sc, m, d, rec, rng, att, out_dir)) {  // lib.rs:111-114
+    v3 emitted;
+    if (!material_shade(sc, m, d, rec, rng, emitted, att, out_dir)) {  // lib.rs:107-114
       L = T * emitted;
       return true;
     }

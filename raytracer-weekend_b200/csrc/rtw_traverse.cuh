@@ -93,6 +93,42 @@ __device__ __forceinline__ bool slab(float4 lo, float4 hi, v3 o, v3 inv, float t
   return t_min <= t_far;
 }
 
+// The same cull with one FFMA per plane: t = b * inv + (-o * inv).  This is NOT the reference's expression, so its
+// result may differ from the exact-arithmetic slab distance T = (b - o) / d by
+//     |t - T| <= |T| * 3u + |o * inv| * 1.5u        (u = 2^-24: roundings of inv, of o * inv and of the FFMA)
+// — a relative part and an ABSOLUTE part (cancellation when the plane is near the origin).  A box may only be skipped
+// when the exact interval is empty, so the far distance is pushed out by both: relative 2^-20 of |near| + |far|, absolute
+// 2 * slack with slack = 2^-22 * max over the axes of |o * inv| (per ray, RaySlab::set).  On an axis with d = 0 the
+// products are +-inf / NaN exactly as in the reference's form or NaN where that had +-inf: fminf / fmaxf drop NaNs,
+// which can only keep a box, never lose one.  Half the instructions of slab(): 6 FFMA + 6 FMNMX + 2 FMNMX3 per box.
+#ifndef RTW_SLAB_FMA
+#define RTW_SLAB_FMA 0  // r02 A/B: cow 12.15 -> 12.06 ms, jumpy 4.54 -> 4.49, monument 18.9 -> 31.7 (the absolute slack of far-away origins un-culls the tree): off
+#endif
+struct RaySlab {
+  v3 inv, nc;    // 1 / d (aabb.rs:29), -(o * inv)
+  float slack2;  // 2 x the absolute slack
+  __device__ __forceinline__ void set(v3 o, v3 d) {
+    inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    const v3 c = mk(o.x * inv.x, o.y * inv.y, o.z * inv.z);
+    nc = mk(-c.x, -c.y, -c.z);
+    const float INF = __int_as_float(0x7f800000);
+    // axes whose product is not finite (d = 0) contribute no slack: their distances are +-inf / NaN, not rounded values
+    const float ax = fabsf(c.x) < INF ? fabsf(c.x) : 0.0f, ay = fabsf(c.y) < INF ? fabsf(c.y) : 0.0f,
+                az = fabsf(c.z) < INF ? fabsf(c.z) : 0.0f;
+    slack2 = fmaxf(fmaxf(ax, ay), az) * 4.76837158e-7f;  // 2 * 2^-22
+  }
+};
+__device__ __forceinline__ bool slab_fma(float4 lo, float4 hi, const RaySlab& rs, float t_min, float t_max, float& t_near) {
+  const float x0 = __fmaf_rn(lo.x, rs.inv.x, rs.nc.x), x1 = __fmaf_rn(hi.x, rs.inv.x, rs.nc.x);
+  const float y0 = __fmaf_rn(lo.y, rs.inv.y, rs.nc.y), y1 = __fmaf_rn(hi.y, rs.inv.y, rs.nc.y);
+  const float z0 = __fmaf_rn(lo.z, rs.inv.z, rs.nc.z), z1 = __fmaf_rn(hi.z, rs.inv.z, rs.nc.z);
+  const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), t_min));
+  const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), t_max));
+  t_near = tn;
+  const float far_out = __fmaf_rn(fabsf(tn) + fabsf(tf), 9.53674316e-7f, tf) + rs.slack2;
+  return tn <= far_out;
+}
+
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 struct TraverseCounters {
@@ -150,6 +186,13 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
   // per-ray state
   uint32_t index = 0;
   v3 o = mk(0, 0, 0), d = mk(0, 0, 0), inv = mk(0, 0, 0), oi = o, di = d;
+  RaySlab rs;
+  rs.inv = inv; rs.nc = inv; rs.slack2 = 0.f;
+#if RTW_SLAB_FMA
+#define RTW_SLAB(lo, hi, tmin, tmax, tnear) slab_fma(lo, hi, rs, tmin, tmax, tnear)
+#else
+#define RTW_SLAB(lo, hi, tmin, tmax, tnear) slab(lo, hi, o, inv, tmin, tmax, tnear)
+#endif
   float time = 0.f, t_min = 0.f, best_t = 0.f;
   int32_t best_slot = -1, best_id = -2, link = RTW_LINK_DONE, pl_link = 0;
   uint32_t best_meta = 0, meta = 0, pl_meta = 0, cur_inst = 0, cur_pm = 0xffffffffu;
@@ -204,7 +247,11 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
         float t_max;
         int32_t slot0 = -1;
         if (index < count && io.load(index, o, d, time, t_min, t_max, slot0, resumed)) {
+#if RTW_SLAB_FMA
+          rs.set(o, d);
+#else
           inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);  // aabb.rs:29
+#endif
           best_t = t_max; best_slot = slot0; best_id = -2;
           best_meta = slot0 >= 0 ? __ldg(sc.slot_meta + slot0) : 0u;
           oi = o; di = d; cur_inst = 0; cur_pm = 0xffffffffu;
@@ -257,7 +304,7 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
           const float4 lo = __ldg(n + 2 * c), hi = __ldg(n + 2 * c + 1);
           float t;
           const int32_t l = __float_as_int(lo.w);
-          const bool h = (l != RTW_LINK_DONE) && slab(lo, hi, o, inv, t_min, best_t, t);
+          const bool h = (l != RTW_LINK_DONE) && RTW_SLAB(lo, hi, t_min, best_t, t);
           lk[c] = h ? l : RTW_LINK_DONE;
           tk[c] = h ? t : INF;
           mk4[c] = __float_as_uint(hi.w);
@@ -304,8 +351,8 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
         const int32_t rl = (b.w & 0x80000000u) ? ~(int32_t)(b.w & 0x3FFFFFFu) : (int32_t)b.w;
         const uint32_t lm = ((a.w >> 26) & 31u) + 1u, rm = ((b.w >> 26) & 31u) + 1u;
         float tl, tr;
-        const bool hl = slab(l0, l1, o, inv, t_min, best_t, tl);
-        const bool hr = slab(r0, r1, o, inv, t_min, best_t, tr);
+        const bool hl = RTW_SLAB(l0, l1, t_min, best_t, tl);
+        const bool hr = RTW_SLAB(r0, r1, t_min, best_t, tr);
         if (hl && hr) {
           const bool left_first = tl <= tr;
           stack[sp++] = left_first ? stack_pack(rl, rm) : stack_pack(ll, lm);
@@ -342,8 +389,8 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
 #endif
         if (COUNT) cnt.pairs++;
         float tl, tr;
-        const bool hl = slab(l0, l1, o, inv, t_min, best_t, tl);
-        const bool hr = slab(r0, r1, o, inv, t_min, best_t, tr);
+        const bool hl = RTW_SLAB(l0, l1, t_min, best_t, tl);
+        const bool hr = RTW_SLAB(r0, r1, t_min, best_t, tr);
         if (hl && hr) {
           const bool left_first = tl <= tr;
           const int2 far = left_first ? make_int2(__float_as_int(r0.w), __float_as_int(r1.w))
