@@ -113,7 +113,7 @@ struct FrameDev {
   uint32_t seed_lo, seed_hi;
   unsigned long long pix_per_slice;  // owned tiles * tile_size^2 (includes out-of-image padding)
   unsigned long long n_items;
-  uint32_t fit32;         // n_items, nsamp * slices < 2^32: decode_item stays in 32-bit arithmetic
+  uint32_t pad0;
   uint32_t tile_shift;    // log2(tile_size) when it is a power of two, else 0xffffffff
   uint32_t skip_unowned;  // k_wave_resolve leaves the pixels of other partitions untouched (multi-GPU: one shared frame)
   uint32_t pad;
@@ -156,36 +156,28 @@ struct Item {
   uint32_t sample, sample_end, slice;
 };
 
-__device__ __forceinline__ bool decode_item(const FrameDev& f, unsigned long long n, Item& it) {
-  uint32_t k, tile_local, within, tx, ty, wx, wy;
-  if (f.fit32) {  // warp-uniform; 64-bit divisions cost ~100 instructions each
-    const uint32_t n32 = (uint32_t)n, pps = (uint32_t)f.pix_per_slice;
-    k = n32 / pps;
-    const uint32_t q = n32 - k * pps;
-    if (f.tile_shift != 0xffffffffu) {
-      tile_local = q >> (2u * f.tile_shift);
-      within = q & ((1u << (2u * f.tile_shift)) - 1u);
-      wx = within & (f.tile_size - 1u);
-      wy = within >> f.tile_shift;
-    } else {
-      const uint32_t tsq = f.tile_size * f.tile_size;
-      tile_local = q / tsq; within = q - tile_local * tsq;
-      wy = within / f.tile_size; wx = within - wy * f.tile_size;
-    }
-    it.sample = f.sample_begin + (f.nsamp * k) / f.slices;
-    it.sample_end = f.sample_begin + (f.nsamp * (k + 1u)) / f.slices;
+// (render_device guarantees n_items < 2^32 and nsamp * (slices + 1) < 2^32: everything stays in 32-bit arithmetic —
+// a 64-bit division costs ~100 instructions and r01 carried a second, 64-bit copy of this function in every kernel)
+__device__ __forceinline__ bool decode_item(const FrameDev& f, uint32_t n, Item& it) {
+  uint32_t tile_local, within, wx, wy;
+  const uint32_t pps = (uint32_t)f.pix_per_slice;
+  const uint32_t k = n / pps;
+  const uint32_t q = n - k * pps;
+  if (f.tile_shift != 0xffffffffu) {
+    tile_local = q >> (2u * f.tile_shift);
+    within = q & ((1u << (2u * f.tile_shift)) - 1u);
+    wx = within & (f.tile_size - 1u);
+    wy = within >> f.tile_shift;
   } else {
-    k = (uint32_t)(n / f.pix_per_slice);
-    const unsigned long long q = n % f.pix_per_slice;
     const uint32_t tsq = f.tile_size * f.tile_size;
-    tile_local = (uint32_t)(q / tsq); within = (uint32_t)(q % tsq);
-    wy = within / f.tile_size; wx = within % f.tile_size;
-    it.sample = f.sample_begin + (uint32_t)(((unsigned long long)f.nsamp * k) / f.slices);
-    it.sample_end = f.sample_begin + (uint32_t)(((unsigned long long)f.nsamp * (k + 1)) / f.slices);
+    tile_local = q / tsq; within = q - tile_local * tsq;
+    wy = within / f.tile_size; wx = within - wy * f.tile_size;
   }
+  it.sample = f.sample_begin + (f.nsamp * k) / f.slices;
+  it.sample_end = f.sample_begin + (f.nsamp * (k + 1u)) / f.slices;
   const unsigned long long tile = (unsigned long long)tile_local * f.part_count + f.part_rank;
   if (tile >= f.tiles_total) return false;
-  ty = (uint32_t)tile / f.tiles_x; tx = (uint32_t)tile - ty * f.tiles_x;
+  const uint32_t ty = (uint32_t)tile / f.tiles_x, tx = (uint32_t)tile - ty * f.tiles_x;
   const uint32_t x = tx * f.tile_size + wx;
   const uint32_t y_top = ty * f.tile_size + wy;
   if (x >= f.width || y_top >= f.height) return false;
@@ -227,7 +219,7 @@ __device__ __forceinline__ bool fetch_item(const FrameDev& f, WaveCtl* ctl, bool
     }
     if (need && !got) {
       unsigned long long n = base + __popc(m & ((1u << lane) - 1u));
-      if (n < f.n_items) got = decode_item(f, n, it);
+      if (n < f.n_items) got = decode_item(f, (uint32_t)n, it);
       else need = false;
     }
   }
@@ -515,9 +507,10 @@ __global__ void __launch_bounds__(128) k_wave_shade(
   if (lane == 0) grabbed = atomicAdd(&ctl->cursor_shade, 32u);
   for (;;) {
     const uint32_t base = __shfl_sync(0xffffffffu, grabbed, 0);
-    if (base >= count) break;
+    const bool more = base < count;  // warp-uniform: another trip of 32 entries
+    if (!more && nback == 0) break;
     const uint32_t i = base + lane;
-    bool active = i < count;
+    bool active = more && i < count;
     uint32_t slot = 0;
     bool alive = false;  // slot continues into the next iteration
     bool ended = false;  // the path ended: restart the slot (next sample of its item, or a new item)
@@ -575,7 +568,7 @@ __global__ void __launch_bounds__(128) k_wave_shade(
         }
       }
     }
-    if (out_queue) queue_push(next_queue, next_count, alive, slot);
+    if (out_queue && more) queue_push(next_queue, next_count, alive, slot);
     const uint32_t m_end = __ballot_sync(0xffffffffu, ended);
     if (ended) {
       const uint32_t pos = nback + __popc(m_end & lane_lt);
@@ -584,13 +577,15 @@ __global__ void __launch_bounds__(128) k_wave_shade(
     }
     nback += __popc(m_end);
     __syncwarp();
-    if (lane == 0) grabbed = atomicAdd(&ctl->cursor_shade, 32u);
-    if (nback >= 32u) {
-      nback -= 32u;
-      regenerate(f, w, bl, nback + lane, true, next_queue, next_count, out_queue, new_paths);
+    if (more && lane == 0) grabbed = atomicAdd(&ctl->cursor_shade, 32u);
+    // restart 32 waiting paths together — or, once the entries have run out, whatever is left (ONE call site: the
+    // restart code is a fifth of the kernel)
+    if (nback >= 32u || !more) {
+      const uint32_t take = min(nback, 32u);
+      nback -= take;
+      regenerate(f, w, bl, nback + lane, lane < take, next_queue, next_count, out_queue, new_paths);
     }
   }
-  if (nback > 0) regenerate(f, w, bl, lane, lane < nback, next_queue, next_count, out_queue, new_paths);
   for (int off = 16; off > 0; off >>= 1) {
     new_paths += __shfl_xor_sync(0xffffffffu, new_paths, off);
     nseg += __shfl_xor_sync(0xffffffffu, nseg, off);
@@ -929,7 +924,8 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
   if (slices > 0xFFFFFFu) return set_error(RTW_ERR_INVALID, "render: too many slices");
   f.slices = slices;
   f.n_items = (nsamp == 0) ? 0ull : f.pix_per_slice * slices;
-  f.fit32 = (f.n_items < (1ull << 32) && (unsigned long long)nsamp * (slices + 1ull) < (1ull << 32)) ? 1u : 0u;
+  if (f.n_items >= (1ull << 32) || (unsigned long long)nsamp * (slices + 1ull) >= (1ull << 32))
+    return set_error(RTW_ERR_INVALID, "render: more than 2^32 work items (pixels x slices): use fewer slices");
   f.tile_shift = 0xffffffffu;
   if ((f.tile_size & (f.tile_size - 1u)) == 0u) {
     f.tile_shift = 0;
