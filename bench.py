@@ -440,7 +440,8 @@ class Bench:
         p_tim = part(scene.params(w, h, spp, seed=SEED, pool_size=args.pool, slices=args.slices, flags=rtw.RTW_RENDER_TIME_KERNELS))
         stt = scene.render_device(cam, p_tim, accum.data_ptr(), self.stream.cuda_stream)
         seg_per_launch = stt.segments / max(stt.iterations, 1)
-        share_t = stt.ms_traverse / max(stt.ms_traverse + stt.ms_shade, 1e-9)
+        ms_all = max(stt.ms_traverse + stt.ms_shade + stt.ms_sort, 1e-9)
+        share_t = stt.ms_traverse / ms_all
         # bytes that must cross HBM per segment:
         #   traverse: ray read 32 B + hit record written 8 B; + node and primitive records when the scene exceeds L2
         #   shade:    6 state streams read (hit 8, origin 16, direction 16, throughput 16, state 16, sum 16 = 88 B) and 4
@@ -449,7 +450,8 @@ class Bench:
         scene_s = 0.0 if resident else (4 + 8 + 32 + 48 + 64)
         kernels = {
             "k_wave_traverse": {"ms": stt.ms_traverse, "bytes_per_segment": 40.0 + scene_t, "share": share_t},
-            "k_wave_shade": {"ms": stt.ms_shade, "bytes_per_segment": 152.0 + scene_s, "share": 1.0 - share_t},
+            "k_wave_shade": {"ms": stt.ms_shade, "bytes_per_segment": 152.0 + scene_s + (4.0 if stt.ray_sort else 0.0),
+                             "share": stt.ms_shade / ms_all},
         }
         name = max(kernels, key=lambda k: kernels[k]["share"])
         res = {}
@@ -469,6 +471,9 @@ class Bench:
         r["peak_source"] = self.peak_src
         r["pairs_per_segment"], r["prim_tests_per_segment"], r["node_record_bytes"] = pairs, prims, node_bytes
         r["scene_bytes"] = dev_bytes
+        if stt.ray_sort:  # rtw_raysort.cuh: the iteration's rays are traced in scene-cell order (hierarchies beyond the caches)
+            r["ray_sort"] = {"share_of_step": stt.ms_sort / ms_all, "ms_per_iteration": stt.ms_sort / max(stt.iterations, 1),
+                             "kernels": "k_raysort_hist / _scan / _scatter (one 8-bit LSD pass over the slot keys)"}
         r["other_kernel"] = res["k_wave_shade" if name == "k_wave_traverse" else "k_wave_traverse"]
         r["note"] = (("scene (%d B) is L1/L2 resident: node / primitive fetches never reach HBM, only the wavefront state streams do"
                       % dev_bytes) if resident else

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define RTW_ABI_VERSION 2 /* 2: rtw_render_params.gpus, rtw_render_stats.fused / gpus, rtw_scene_clone */
+#define RTW_ABI_VERSION 3 /* 2: rtw_render_params.gpus, rtw_render_stats.fused / gpus, rtw_scene_clone; 3: rtw_render_stats.ms_sort / ray_sort */
 
 /* error codes */
 #define RTW_OK 0
@@ -122,6 +122,9 @@ typedef struct rtw_render_stats {
   uint32_t fused;         /* 1: one-leaf scene rendered by the fused persistent kernel (no   */
                           /*   wavefront, one launch per frame)                              */
   uint32_t gpus;          /* devices that rendered this frame                               */
+  float ms_sort;          /* summed CUDA-event time of the ray-reordering passes (if timed)  */
+  uint32_t ray_sort;      /* 1: the rays of every iteration were traced in scene-cell order  */
+                          /*   (hierarchies that do not fit the caches; same frame bits)      */
 } rtw_render_stats;
 
 typedef struct rtw_build_stats {

@@ -60,7 +60,7 @@ class RenderStats(C.Structure):
                 ("prim_bytes", C.c_uint64),
                 ("iterations", C.c_uint32), ("launches", C.c_uint32), ("pool_size", C.c_uint32), ("slices", C.c_uint32),
                 ("ms_render", C.c_float), ("ms_traverse", C.c_float), ("ms_shade", C.c_float), ("node_record_bytes", C.c_float),
-                ("fused", C.c_uint32), ("gpus", C.c_uint32)]
+                ("fused", C.c_uint32), ("gpus", C.c_uint32), ("ms_sort", C.c_float), ("ray_sort", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -35,6 +35,7 @@
 
 #include "rtw_scene.cuh"
 #include "rtw_traverse.cuh"
+#include "rtw_raysort.cuh"
 
 namespace rtw {
 
@@ -101,6 +102,9 @@ struct WaveDev {
   float4* partial;  // [slices][pix_per_slice] slice sums of the pixels this partition owns (slices > 1)
   WaveCtl* ctl;
   uint32_t slot_count;
+  // ray reordering (rtw_raysort.cuh); both null when off
+  uint32_t* sort_key;     // [slot] key of the ray the slot holds, written with the ray
+  const uint32_t* order;  // the entries of the iteration in key order: what the traversal kernel walks
 };
 
 struct FrameDev {
@@ -118,21 +122,26 @@ struct FrameDev {
   uint32_t skip_unowned;  // k_wave_resolve leaves the pixels of other partitions untouched (multi-GPU: one shared frame)
   uint32_t pad;
   float* accum;           // the frame: width*height*3 sums (this device's memory, or a peer's over NVLink)
+  RaySortGrid sort;       // scene box for the ray keys (rtw_raysort.cuh)
 };
 
 // the traversal kernel variants a wavefront render can launch
-enum TravKind { TK_PAIR = 0, TK_MEDIA, TK_WIDE, TK_COMPACT, TK_COUNT, TK_COUNT_COMPACT, TK_FLAT, TK_N };
+enum TravKind { TK_PAIR = 0, TK_MEDIA, TK_WIDE, TK_COMPACT, TK_COUNT, TK_COUNT_COMPACT, TK_FLAT,
+                TK_POOL_PAIR, TK_POOL_COMPACT, TK_POOL_COUNT_PAIR, TK_POOL_COUNT_COMPACT, TK_N };
 
 struct GraphKey {
-  int kind = -1, batch = 0, grid_t = 0, grid_s = 0;
+  int kind = -1, batch = 0, grid_t = 0, grid_s = 0, sort = 0;
   uint32_t pool = 0;
   bool operator==(const GraphKey& o) const {
-    return kind == o.kind && batch == o.batch && grid_t == o.grid_t && grid_s == o.grid_s && pool == o.pool;
+    return kind == o.kind && batch == o.batch && grid_t == o.grid_t && grid_s == o.grid_s && pool == o.pool && sort == o.sort;
   }
 };
 
 struct WaveHost {
   WaveDev dev{};
+  RaySortDev rsort{};              // ray reordering scratch (allocated with the pool on first use)
+  uint32_t rsort_pool = 0;
+  int rsort_blocks = 0;
   std::vector<void*> pool_allocs;
   uint32_t pool = 0;               // slots the pool arrays hold
   float4* partial = nullptr;
@@ -240,6 +249,7 @@ __device__ __forceinline__ void start_path(const FrameDev& f, const WaveDev& w, 
   w.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.f);
   w.thr[slot] = make_float4(1.f, 1.f, 1.f, 0.f);
   w.state[slot] = make_uint4(it.pixel, it.sample, it.sample_end, it.slice << 8);
+  if (w.sort_key) w.sort_key[slot] = ray_sort_key(f.sort, o, d);
 }
 
 // the slice sum of a finished work item: straight into the frame (one slice) or into the slice-sum buffer
@@ -332,6 +342,7 @@ __global__ void __launch_bounds__(128) k_wave_init(SceneDev sc, const FrameDev* 
     w.sum[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
   } else if (tid < w.slot_count) {
     w.ray_d[slot] = make_float4(0.f, 0.f, 0.f, RTW_SLOT_DEAD);
+    if (w.sort_key) w.sort_key[slot] = RTW_RAYSORT_DEAD_KEY;
   }
   uint32_t m = __ballot_sync(0xffffffffu, got);
   if ((threadIdx.x & 31) == 0 && m) atomicAdd(&w.ctl->paths, (unsigned long long)__popc(m));
@@ -405,7 +416,7 @@ __global__ void __launch_bounds__(128, 8) k_wave_traverse_flat(SceneDev sc, cons
   uint32_t count, in_queue;
   traverse_prologue(w, parity, count, in_queue);
   stage_flat(sc, fr);
-  WaveIO io{w, in_queue ? w.queue[parity] : nullptr, 0, fp, false};
+  WaveIO io{w, w.order ? w.order : (in_queue ? w.queue[parity] : nullptr), 0, fp, false};
   traverse_flat(sc, fr, io, count, &w.ctl->cursor_traverse);
 }
 
@@ -417,7 +428,7 @@ __global__ void __launch_bounds__(128, (COUNT || MEDIA || NODES == NODES_WIDE) ?
   traverse_prologue(w, parity, count, in_queue);
   const uint32_t lane = threadIdx.x & 31;
   TraverseCounters cnt;
-  WaveIO io{w, in_queue ? w.queue[parity] : nullptr, 0, fp, false};
+  WaveIO io{w, w.order ? w.order : (in_queue ? w.queue[parity] : nullptr), 0, fp, false};
 #if RTW_TOP_TREE > 0
   __shared__ float4 top_smem[4 * RTW_TOP_TREE];
   stage_top_tree(sc, top_smem);
@@ -425,6 +436,33 @@ __global__ void __launch_bounds__(128, (COUNT || MEDIA || NODES == NODES_WIDE) ?
 #else
   traverse_persistent<COUNT, MEDIA, NODES>(sc, io, count, &ctl->cursor_traverse, cnt);
 #endif
+  if (COUNT) {
+    uint32_t p = cnt.pairs, q = cnt.prims, r = cnt.prim_bytes;
+    for (int off = 16; off > 0; off >>= 1) {
+      p += __shfl_xor_sync(0xffffffffu, p, off);
+      q += __shfl_xor_sync(0xffffffffu, q, off);
+      r += __shfl_xor_sync(0xffffffffu, r, off);
+    }
+    if (lane == 0) {
+      atomicAdd(&ctl->pairs, (unsigned long long)p);
+      atomicAdd(&ctl->prims, (unsigned long long)q);
+      atomicAdd(&ctl->prim_bytes, (unsigned long long)r);
+    }
+  }
+}
+
+// The walk with pooled leaf tests (rtw_traverse.cuh: traverse_pooled): scenes without media
+template <bool COUNT, int NODES>
+__global__ void __launch_bounds__(128, COUNT ? 1 : RTW_TRAVERSE_MINBLOCKS)
+    k_wave_traverse_pooled(SceneDev sc, const FrameDev* __restrict__ fp, WaveDev w, uint32_t parity) {
+  __shared__ LeafPool pools[4];
+  WaveCtl* ctl = w.ctl;
+  uint32_t count, in_queue;
+  traverse_prologue(w, parity, count, in_queue);
+  const uint32_t lane = threadIdx.x & 31;
+  TraverseCounters cnt;
+  WaveIO io{w, w.order ? w.order : (in_queue ? w.queue[parity] : nullptr), 0, fp, false};
+  traverse_pooled<COUNT, NODES>(sc, io, count, &ctl->cursor_traverse, cnt, pools[threadIdx.x >> 5]);
   if (COUNT) {
     uint32_t p = cnt.pairs, q = cnt.prims, r = cnt.prim_bytes;
     for (int off = 16; off > 0; off >>= 1) {
@@ -475,6 +513,7 @@ __device__ __forceinline__ void regenerate(const FrameDev& f, const WaveDev& w, 
     new_paths++;
   } else if (valid) {
     w.ray_d[slot] = make_float4(0.f, 0.f, 0.f, RTW_SLOT_DEAD);  // no work left for this slot
+    if (w.sort_key) w.sort_key[slot] = RTW_RAYSORT_DEAD_KEY;
   }
   if (out_queue) queue_push(next_queue, next_count, go, slot);
 }
@@ -554,6 +593,7 @@ __global__ void __launch_bounds__(128) k_wave_shade(
           w.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.f);
           w.thr[slot] = make_float4(T.x, T.y, T.z, 0.f);
           w.state[slot] = make_uint4(st.x, st.y, st.z, (st.w & ~0xffu) | bounce);
+          if (w.sort_key) w.sort_key[slot] = ray_sort_key(f.sort, o, d);
           alive = true;
         }
       }
@@ -738,6 +778,18 @@ __global__ void k_resolve_rgb8(const float* __restrict__ accum, size_t n, float 
   }
 }
 
+// debug (RTW_RAYSORT_CHECK=1, instrumented path): inversions of order[] and entries that are not a permutation
+__global__ void k_raysort_check(const uint32_t* __restrict__ count, const uint32_t* __restrict__ key, const uint32_t* __restrict__ order,
+                                unsigned long long* __restrict__ out) {
+  const uint32_t n = *count;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i + 1 < n; i += gridDim.x * blockDim.x) {
+    const uint32_t mask = (1u << RTW_RAYSORT_KEY_BITS) - 1u;  // the passes sort these bits (a dead slot's key is all ones)
+    if ((key[order[i]] & mask) > (key[order[i + 1]] & mask)) atomicAdd(&out[0], 1ull);
+    if ((key[order[i]] & mask) != (key[order[i + 1]] & mask)) atomicAdd(&out[1], 1ull);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&out[2], (unsigned long long)n);
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------------
 template <class T>
 int wave_alloc(std::vector<void*>* bag, T** out, size_t count) {
@@ -766,6 +818,8 @@ void release_pool(WaveHost* wh) {
   for (void* p : wh->pool_allocs) cudaFree(p);
   wh->pool_allocs.clear();
   wh->pool = 0;
+  wh->rsort = RaySortDev{};
+  wh->rsort_pool = 0;
   float4* keep = wh->dev.partial;
   WaveCtl* ctl = wh->dev.ctl;
   wh->dev = WaveDev{};
@@ -812,7 +866,9 @@ int create_wave(rtw_scene* s, WaveHost** out) {
   const void* kernels[TK_N] = {(const void*)k_wave_traverse<false, false, NODES_PAIR>, (const void*)k_wave_traverse<false, true, NODES_PAIR>,
                                (const void*)k_wave_traverse<false, false, NODES_WIDE>, (const void*)k_wave_traverse<false, false, NODES_COMPACT>,
                                (const void*)k_wave_traverse<true, true, NODES_PAIR>, (const void*)k_wave_traverse<true, true, NODES_COMPACT>,
-                               (const void*)k_wave_traverse_flat};
+                               (const void*)k_wave_traverse_flat,
+                               (const void*)k_wave_traverse_pooled<false, NODES_PAIR>, (const void*)k_wave_traverse_pooled<false, NODES_COMPACT>,
+                               (const void*)k_wave_traverse_pooled<true, NODES_PAIR>, (const void*)k_wave_traverse_pooled<true, NODES_COMPACT>};
   for (int k = 0; k < TK_N; ++k) {
     RTW_WAVE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernels[k], 128, 0));
     wh->blocks_trav[k] = std::max(nb, 1) * s->num_sms;
@@ -964,6 +1020,34 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
       wh->pool = pool;
     }
   }
+  // Ray reordering between iterations (rtw_raysort.cuh): on for hierarchies that live in HBM (compact pairs exist),
+  // RTW_RAYSORT=0/1 overrides.
+  bool raysort = !mega && !flat && s->dev.nodes_c != nullptr && !s->dev.has_media;
+  if (const char* e = getenv("RTW_RAYSORT")) raysort = !mega && !flat && atoi(e) != 0;
+  if (raysort && wh->rsort_pool < wh->pool) {
+    drop_graph(wh);
+    RaySortDev& r = wh->rsort;
+    wh->rsort_blocks = std::min(RTW_RAYSORT_MAX_BLOCKS, 8 * s->num_sms);
+    int rc;
+    if ((rc = wave_alloc(&wh->pool_allocs, &r.key, wh->pool)) || (rc = wave_alloc(&wh->pool_allocs, &r.keys[0], wh->pool)) ||
+        (rc = wave_alloc(&wh->pool_allocs, &r.keys[1], wh->pool)) || (rc = wave_alloc(&wh->pool_allocs, &r.vals[0], wh->pool)) ||
+        (rc = wave_alloc(&wh->pool_allocs, &r.vals[1], wh->pool)) ||
+        (rc = wave_alloc(&wh->pool_allocs, &r.hist, (size_t)256 * RTW_RAYSORT_MAX_BLOCKS)) ||
+        (rc = wave_alloc(&wh->pool_allocs, &r.totals, (size_t)256))) {
+      release_pool(wh);
+      return rc;
+    }
+    wh->rsort_pool = wh->pool;
+  }
+  wh->dev.sort_key = raysort ? wh->rsort.key : nullptr;
+  wh->dev.order = raysort ? wh->rsort.vals[(RTW_RAYSORT_PASSES - 1) & 1] : nullptr;
+  f.sort.enabled = raysort ? 1u : 0u;
+  for (int a = 0; a < 3; ++a) {
+    const float lo = s->root_box[a], hi = s->root_box[3 + a];
+    f.sort.lo[a] = lo;
+    f.sort.hi[a] = hi;
+    f.sort.scale[a] = (hi > lo) ? 1024.0f / (hi - lo) : 0.0f;
+  }
   const size_t partial_elems = slices > 1 ? (size_t)slices * f.pix_per_slice : 0;
   if (wh->partial_elems < partial_elems) {
     drop_graph(wh);
@@ -988,8 +1072,13 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
     wide = atoi(e) != 0 && s->dev.nodes4 != nullptr && !s->dev.has_media && 3u * (s->bvh_height / 2u + 1u) + 2u <= RTW_STACK_SIZE;
   // compact pairs exist only when rtw_build found the hierarchy too large for the caches (rtw_bvh.cu)
   const bool compact = s->dev.nodes_c != nullptr && !s->dev.has_media;
-  const TravKind kind = count_trav ? (compact ? TK_COUNT_COMPACT : TK_COUNT)
-                                   : (s->dev.has_media ? TK_MEDIA : (flat ? TK_FLAT : (compact ? TK_COMPACT : (wide ? TK_WIDE : TK_PAIR))));
+  // leaf tests pooled per warp (traverse_pooled): every hierarchy without media; RTW_POOLED=0 selects the per-lane walk
+  bool pooled = !s->dev.has_media && !flat && !wide && s->dev.num_prims < (1u << 27);
+  if (const char* e = getenv("RTW_POOLED")) pooled = pooled && atoi(e) != 0;
+  else pooled = false;  // measured slower (profiles/r02_sweeps.txt): experiment only
+  const TravKind kind = pooled ? (count_trav ? (compact ? TK_POOL_COUNT_COMPACT : TK_POOL_COUNT_PAIR) : (compact ? TK_POOL_COMPACT : TK_POOL_PAIR))
+                               : (count_trav ? (compact ? TK_COUNT_COMPACT : TK_COUNT)
+                                             : (s->dev.has_media ? TK_MEDIA : (flat ? TK_FLAT : (compact ? TK_COMPACT : (wide ? TK_WIDE : TK_PAIR)))));
   const FrameDev* dfp = wh->d_frame;
   auto launch_traverse = [&](uint32_t parity, int grid) {
     switch (kind) {
@@ -999,14 +1088,42 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
       case TK_COMPACT: k_wave_traverse<false, false, NODES_COMPACT><<<grid, 128, 0, st>>>(s->dev, dfp, w, parity); break;
       case TK_COUNT: k_wave_traverse<true, true, NODES_PAIR><<<grid, 128, 0, st>>>(s->dev, dfp, w, parity); break;
       case TK_FLAT: k_wave_traverse_flat<<<grid, 128, 0, st>>>(s->dev, dfp, w, parity); break;
+      case TK_POOL_PAIR: k_wave_traverse_pooled<false, NODES_PAIR><<<grid, 128, 0, st>>>(s->dev, dfp, w, parity); break;
+      case TK_POOL_COMPACT: k_wave_traverse_pooled<false, NODES_COMPACT><<<grid, 128, 0, st>>>(s->dev, dfp, w, parity); break;
+      case TK_POOL_COUNT_PAIR: k_wave_traverse_pooled<true, NODES_PAIR><<<grid, 128, 0, st>>>(s->dev, dfp, w, parity); break;
+      case TK_POOL_COUNT_COMPACT: k_wave_traverse_pooled<true, NODES_COMPACT><<<grid, 128, 0, st>>>(s->dev, dfp, w, parity); break;
       default: k_wave_traverse<true, true, NODES_COMPACT><<<grid, 128, 0, st>>>(s->dev, dfp, w, parity); break;
     }
   };
+
+  // order[] for the iteration of this parity: LSD radix passes over (key[slot], slot) of its entry list
+  auto launch_sort = [&](uint32_t parity) {
+    const RaySortDev& r = wh->rsort;
+    const uint32_t* cnt = &wh->d_ctl->count[parity];
+    const uint32_t* qm = &wh->d_ctl->qmode[parity];
+    const int g = wh->rsort_blocks;
+    for (int ps = 0; ps < RTW_RAYSORT_PASSES; ++ps) {
+      const int shift = 8 * ps;
+      const bool last = ps == RTW_RAYSORT_PASSES - 1;
+      const uint32_t* kin = ps == 0 ? r.key : r.keys[(ps - 1) & 1];
+      const uint32_t* vin = ps == 0 ? nullptr : r.vals[(ps - 1) & 1];
+      if (ps == 0) k_raysort_hist<true><<<g, RTW_RAYSORT_THREADS, 0, st>>>(cnt, qm, w.queue[parity], kin, shift, r.hist);
+      else k_raysort_hist<false><<<g, RTW_RAYSORT_THREADS, 0, st>>>(cnt, qm, nullptr, kin, shift, r.hist);
+      k_raysort_scan<<<256, 1024, 0, st>>>((uint32_t)g, r.hist, r.totals);
+      if (ps == 0 && last) k_raysort_scatter<true, true><<<g, RTW_RAYSORT_THREADS, 0, st>>>(cnt, qm, w.queue[parity], kin, vin, r.keys[ps & 1], r.vals[ps & 1], shift, r.hist, r.totals);
+      else if (ps == 0) k_raysort_scatter<true, false><<<g, RTW_RAYSORT_THREADS, 0, st>>>(cnt, qm, w.queue[parity], kin, vin, r.keys[ps & 1], r.vals[ps & 1], shift, r.hist, r.totals);
+      else if (last) k_raysort_scatter<false, true><<<g, RTW_RAYSORT_THREADS, 0, st>>>(cnt, qm, nullptr, kin, vin, r.keys[ps & 1], r.vals[ps & 1], shift, r.hist, r.totals);
+      else k_raysort_scatter<false, false><<<g, RTW_RAYSORT_THREADS, 0, st>>>(cnt, qm, nullptr, kin, vin, r.keys[ps & 1], r.vals[ps & 1], shift, r.hist, r.totals);
+    }
+  };
+  const uint32_t sort_launches = raysort ? 3u * RTW_RAYSORT_PASSES : 0u;
 
   // All work runs on an internal stream ordered after the caller's stream; the call returns only after that stream has
   // drained, so the caller's stream order is preserved on both sides.
   RTW_CUDA_TRY(cudaEventRecord(wh->ev_in, user_stream));
   RTW_CUDA_TRY(cudaStreamWaitEvent(st, wh->ev_in, 0));
+  unsigned long long* d_check = nullptr;
+  EventBag sev;  // begin/end pairs around the ray-reordering passes of the instrumented path
   EventBag kev;  // begin/end pairs of the instrumented path: traverse, shade, traverse, shade ...
   uint32_t launches = 0, iterations = 0;
   const char* fault = getenv("RTW_FAULT_INJECT");  // tests: "capture" fails inside the graph capture, "launch" launches an invalid grid
@@ -1043,11 +1160,13 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
       key.grid_t = std::min(wh->blocks_trav[kind], std::max(need_blocks, 1));
       key.grid_s = std::min(wh->blocks_shade, std::max(need_blocks, 1));
       key.pool = pool;
+      key.sort = raysort ? 1 : 0;
       if (!(wh->graph_exec && wh->graph_key == key)) {
         drop_graph(wh);
         cudaGraph_t graph = nullptr;
         RTW_CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         for (int b = 0; b < key.batch; ++b) {
+          if (raysort) launch_sort((uint32_t)(b & 1));
           launch_traverse((uint32_t)(b & 1), key.grid_t);
           k_wave_shade<<<key.grid_s, 128, 0, st>>>(s->dev, dfp, w, (uint32_t)(b & 1));
         }
@@ -1067,7 +1186,7 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
         RTW_CUDA_TRY(cudaGraphLaunch(wh->graph_exec, st));
         RTW_CUDA_TRY(cudaMemcpyAsync(&wh->pinned_ctl[i & 1], wh->d_ctl, sizeof(WaveCtl), cudaMemcpyDeviceToHost, st));
         RTW_CUDA_TRY(cudaEventRecord(wh->ring_ev[i & 1], st));
-        launches += 2 * key.batch;
+        launches += (2 + sort_launches) * key.batch;
         iterations += key.batch;
         if (i >= 1) {
           RTW_CUDA_TRY(cudaEventSynchronize(wh->ring_ev[(i - 1) & 1]));
@@ -1076,6 +1195,10 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
       }
     } else {
       // ---- instrumented path (traversal counters / per-kernel CUDA events): plain launches
+      if (raysort && getenv("RTW_RAYSORT_CHECK")) {
+        cudaMalloc((void**)&d_check, 3 * sizeof(unsigned long long));
+        cudaMemsetAsync(d_check, 0, 3 * sizeof(unsigned long long), st);
+      }
       k_wave_init<<<(pool + 127) / 128, 128, 0, st>>>(s->dev, dfp, w);
       launches++;
       uint32_t parity = 0;
@@ -1083,10 +1206,20 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
       for (;;) {
         for (int b = 0; b < batch; ++b) {
           cudaEvent_t e4[4] = {nullptr, nullptr, nullptr, nullptr};
+          if (raysort) {
+            cudaEvent_t es[2] = {nullptr, nullptr};
+            if (time_kernels) {
+              for (auto& e : es) RTW_CUDA_TRY(sev.add(&e));
+              RTW_CUDA_TRY(cudaEventRecord(es[0], st));
+            }
+            launch_sort(parity);
+            if (time_kernels) RTW_CUDA_TRY(cudaEventRecord(es[1], st));
+          }
           if (time_kernels) {
             for (auto& e : e4) RTW_CUDA_TRY(kev.add(&e));
             RTW_CUDA_TRY(cudaEventRecord(e4[0], st));
           }
+          if (raysort && d_check) k_raysort_check<<<1184, 256, 0, st>>>(&wh->d_ctl->count[parity], wh->rsort.key, w.order, d_check);
           launch_traverse(parity, wh->blocks_trav[kind]);
           if (time_kernels) {
             RTW_CUDA_TRY(cudaEventRecord(e4[1], st));
@@ -1095,7 +1228,7 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
           k_wave_shade<<<wh->blocks_shade, 128, 0, st>>>(s->dev, dfp, w, parity);
           if (time_kernels) RTW_CUDA_TRY(cudaEventRecord(e4[3], st));
           parity ^= 1;
-          launches += 2;
+          launches += 2 + sort_launches;
           iterations++;
         }
         RTW_CUDA_TRY(cudaMemcpyAsync(wh->pinned_ctl, wh->d_ctl, sizeof(WaveCtl), cudaMemcpyDeviceToHost, st));
@@ -1113,6 +1246,12 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
   RTW_CUDA_TRY(cudaEventRecord(wh->ev_end, st));
   RTW_CUDA_TRY(cudaMemcpyAsync(&wh->pinned_ctl[2], wh->d_ctl, sizeof(WaveCtl), cudaMemcpyDeviceToHost, st));
   RTW_CUDA_TRY(cudaStreamSynchronize(st));
+  if (d_check) {
+    unsigned long long hc[3] = {0, 0, 0};
+    cudaMemcpy(hc, d_check, sizeof(hc), cudaMemcpyDeviceToHost);
+    cudaFree(d_check);
+    fprintf(stdout, "[raysort check] inversions %llu, key changes %llu over %llu sorted entries\n", hc[0], hc[1], hc[2]);
+  }
   const WaveCtl total = wh->pinned_ctl[2];
   float ms = 0.f;
   cudaEventElapsedTime(&ms, wh->ev_begin, wh->ev_end);
@@ -1123,6 +1262,12 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
     cudaEventElapsedTime(&b, kev.v[i + 2], kev.v[i + 3]);
     ms_t += a;
     ms_s += b;
+  }
+  float ms_sort = 0.f;
+  for (size_t i = 0; i + 1 < sev.v.size(); i += 2) {
+    float a = 0.f;
+    cudaEventElapsedTime(&a, sev.v[i], sev.v[i + 1]);
+    ms_sort += a;
   }
   if (stats) {
     memset(stats, 0, sizeof(*stats));
@@ -1140,6 +1285,8 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
     stats->ms_shade = ms_s;
     stats->node_record_bytes = mega ? 0.f : (compact ? 32.f : (wide ? 128.f : 64.f));
     stats->fused = mega ? 1u : 0u;
+    stats->ms_sort = ms_sort;
+    stats->ray_sort = raysort ? 1u : 0u;
   }
   return RTW_OK;
 }

@@ -129,6 +129,32 @@ __device__ __forceinline__ bool slab_fma(float4 lo, float4 hi, const RaySlab& rs
   return tn <= far_out;
 }
 
+// sm_100a: one 256-bit load (LDG.E.256) instead of two LDG.E.128 — a child-pair fetch is the walk's only divergent load
+// and the L1TEX pipeline its busiest unit (r02 captures: 64-75 % busy), so the number of load instructions per step
+// matters, not only the bytes.  p must be 32-byte aligned (pairs are 64-byte records, compact pairs 32-byte records).
+#ifndef RTW_LDG256
+#define RTW_LDG256 1
+#endif
+__device__ __forceinline__ void ldg256(const void* p, float4& a, float4& b) {
+#if RTW_LDG256
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p));
+#else
+  a = __ldg(reinterpret_cast<const float4*>(p));
+  b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+#endif
+}
+__device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
+#if RTW_LDG256
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+#else
+  a = __ldg(reinterpret_cast<const uint4*>(p));
+  b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+#endif
+}
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 struct TraverseCounters {
@@ -175,7 +201,7 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
                                                     TraverseCounters& cnt, const float4* top_smem = nullptr) {
   const uint32_t lane = threadIdx.x & 31;
 #if RTW_TOP_TREE > 0
-  const int32_t root_link = sc.top_count ? (int32_t)RTW_LINK_TOP : 0;
+  const int32_t root_link = (NODES == NODES_PAIR && sc.top_count) ? (int32_t)RTW_LINK_TOP : 0;  // only the fp32-pair walk reads the staged copy
 #else
   const int32_t root_link = 0;
 #endif
@@ -333,7 +359,8 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
       }
       if (NODES == NODES_COMPACT && searching) {
         const uint4* __restrict__ nc = sc.nodes_c + 2 * (size_t)link;
-        const uint4 a = __ldg(nc), b = __ldg(nc + 1);
+        uint4 a, b;
+        ldg256(nc, a, b);
         if (COUNT) cnt.pairs++;
         const float sx = sc.grid_step[0], sy = sc.grid_step[1], sz = sc.grid_step[2];
         const float gx = sc.grid_lo[0], gy = sc.grid_lo[1], gz = sc.grid_lo[2];
@@ -385,7 +412,9 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
         }
 #else
         const float4* __restrict__ n = sc.nodes + 4 * (size_t)link;
-        const float4 l0 = __ldg(n), l1 = __ldg(n + 1), r0 = __ldg(n + 2), r1 = __ldg(n + 3);
+        float4 l0, l1, r0, r1;
+        ldg256(n, l0, l1);
+        ldg256(n + 2, r0, r1);
 #endif
         if (COUNT) cnt.pairs++;
         float tl, tr;
@@ -518,6 +547,223 @@ __device__ __forceinline__ void traverse_persistent(const SceneDev& sc, IO& io, 
       io.store(index, o, d, time, best_slot, best_t, best_meta);
       active = false;
     }
+  }
+}
+
+// ---- pooled leaf tests ----------------------------------------------------------------------------------------------
+// traverse_persistent() above lets every lane test the leaves it reaches itself: measured on the cow scene (r02f capture,
+// tools/ncu_regions.py) the primitive tests are 32 % of the kernel's warp instructions and run at 5.6 of 32 lanes, and
+// the node steps (57 %) at 17 of 32 because lanes that hold a leaf wait for the walkers.  traverse_pooled() separates the
+// two kinds of work inside a warp:
+//   * a lane only WALKS.  When it reaches a leaf it appends (lane, primitive slot) entries to a per-warp FIFO in shared
+//     memory — one primitive per trip — pops its stack and walks on, without waiting for the result;
+//   * as soon as 32 entries are queued the whole warp DRAINS them: lane j tests entry j against its owner's ray (kept in
+//     shared memory), so the primitive tests run at full width whatever leaf each walker is in;
+//   * a hit is merged into its owner's record with one 64-bit shared-memory atomicMin over (ordered t, ~canonical id):
+//     smallest t first, then the LATER primitive of the canonical order — the list rule of hittable/mod.rs:57-69, which
+//     does not depend on the order of the tests.
+// A walker therefore culls with a closest-hit distance that may lag a few steps behind (it can only be too large:
+// culling stays conservative and the result is unchanged); a lane whose stack is empty parks until its last entry has
+// been drained.  A partial batch is drained when RTW_POOL_WAIT_LANES lanes are parked or nothing else can progress.
+#ifndef RTW_POOL_WAIT_LANES
+#define RTW_POOL_WAIT_LANES 8
+#endif
+#ifndef RTW_POOL_SERVICE_LANES
+#define RTW_POOL_SERVICE_LANES 4  // the node loop runs until this many lanes hold a leaf / have finished
+#endif
+#ifndef RTW_POOL_REFILL_IDLE
+#define RTW_POOL_REFILL_IDLE 8
+#endif
+struct LeafPool {  // per warp
+  float ray[8][32];             // world ray of lane's current query: o.xyz, d.xyz, time, t_min
+  unsigned long long best[32];  // (ordered t << 32) | (0xFFFFFFFE - canonical id); low word 0xFFFFFFFF = no hit yet
+  int32_t best_slot[32];
+  uint32_t queue[64];           // (owner lane << 27) | primitive slot
+};
+__device__ __forceinline__ uint32_t float_to_ordered(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_float(uint32_t u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+template <bool COUNT, int NODES, class IO>
+__device__ __forceinline__ void traverse_pooled(const SceneDev& sc, IO& io, uint32_t count, uint32_t* cursor,
+                                                TraverseCounters& cnt, LeafPool& lp) {
+  static_assert(NODES == NODES_PAIR || NODES == NODES_COMPACT, "pooled walk: fp32 pairs or compact pairs");
+  const uint32_t FULL = 0xffffffffu;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t lane_lt = (1u << lane) - 1u;
+  bool active = false;
+  bool parked = false;     // stack empty, entries still queued: waits for a drain
+  bool exhausted = false;  // warp-uniform: the cursor ran past `count`
+  uint32_t index = 0;
+  v3 o = mk(0, 0, 0), d = mk(0, 0, 0), inv = mk(0, 0, 0);
+  float t_min = 0.f, best_t = 0.f, time = 0.f;
+  int32_t link = RTW_LINK_DONE;
+  uint32_t meta = 0;
+  StackEntry stack[RTW_STACK_SIZE];
+  int sp = 0;
+  uint32_t head = 0, tail = 0;  // warp-uniform FIFO counters (monotonic)
+  uint32_t my_last = 0;         // FIFO position just past this lane's last entry
+
+  for (;;) {
+    // ---- (a) refill idle lanes ---------------------------------------------------------------------------------------
+    const uint32_t idle = __ballot_sync(FULL, !active);
+    if (idle != 0 && !exhausted && (__popc(idle) >= RTW_POOL_REFILL_IDLE || idle == FULL)) {
+      const int leader = __ffs(idle) - 1;
+      uint32_t base = 0;
+      if ((int)lane == leader) base = atomicAdd(cursor, (uint32_t)__popc(idle));
+      base = __shfl_sync(FULL, base, leader);
+      if (base + __popc(idle) >= count) exhausted = true;
+      if (!active) {
+        index = base + __popc(idle & lane_lt);
+        float t_max;
+        int32_t slot0 = -1;
+        bool resumed = false;
+        if (index < count && io.load(index, o, d, time, t_min, t_max, slot0, resumed)) {
+          inv = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);  // aabb.rs:29
+          best_t = t_max;
+          lp.ray[0][lane] = o.x; lp.ray[1][lane] = o.y; lp.ray[2][lane] = o.z;
+          lp.ray[3][lane] = d.x; lp.ray[4][lane] = d.y; lp.ray[5][lane] = d.z;
+          lp.ray[6][lane] = time; lp.ray[7][lane] = t_min;
+          const uint32_t low = slot0 >= 0 ? 0xFFFFFFFEu - (uint32_t)__ldg(sc.slot_prim + slot0) : 0xFFFFFFFFu;
+          lp.best[lane] = ((unsigned long long)float_to_ordered(t_max) << 32) | low;
+          lp.best_slot[lane] = slot0;
+          sp = 0; link = 0; meta = 0;
+          my_last = head;
+          active = true;
+        }
+      }
+      __syncwarp();
+    }
+    if (__ballot_sync(FULL, active) == 0) {
+      if (exhausted) break;
+      continue;
+    }
+    // ---- (b) node steps until RTW_POOL_SERVICE_LANES lanes need service (hold a leaf, or are finished) or nobody walks --
+    const uint32_t m_busy = __ballot_sync(FULL, active && !parked);
+    for (;;) {
+      const bool walking = active && link >= 0;
+      const uint32_t m_walk = __ballot_sync(FULL, walking);
+      if (m_walk == 0u || __popc(m_busy & ~m_walk) >= RTW_POOL_SERVICE_LANES) break;
+      if (walking) {
+        float4 l0, l1, r0, r1;
+        int32_t ll, rl;
+        uint32_t lm, rm;
+        if (NODES == NODES_COMPACT) {
+          const uint4* __restrict__ nc = sc.nodes_c + 2 * (size_t)link;
+          uint4 a, b;
+          ldg256(nc, a, b);
+          const float sx = sc.grid_step[0], sy = sc.grid_step[1], sz = sc.grid_step[2];
+          const float gx = sc.grid_lo[0], gy = sc.grid_lo[1], gz = sc.grid_lo[2];
+          // the same expression k_build_compact verified the containment with
+          l0 = make_float4(__fmaf_rn((float)(a.x & 0xffffu), sx, gx), __fmaf_rn((float)(a.x >> 16), sy, gy),
+                           __fmaf_rn((float)(a.y & 0xffffu), sz, gz), 0.f);
+          l1 = make_float4(__fmaf_rn((float)(a.y >> 16), sx, gx), __fmaf_rn((float)(a.z & 0xffffu), sy, gy),
+                           __fmaf_rn((float)(a.z >> 16), sz, gz), 0.f);
+          r0 = make_float4(__fmaf_rn((float)(b.x & 0xffffu), sx, gx), __fmaf_rn((float)(b.x >> 16), sy, gy),
+                           __fmaf_rn((float)(b.y & 0xffffu), sz, gz), 0.f);
+          r1 = make_float4(__fmaf_rn((float)(b.y >> 16), sx, gx), __fmaf_rn((float)(b.z & 0xffffu), sy, gy),
+                           __fmaf_rn((float)(b.z >> 16), sz, gz), 0.f);
+          ll = (a.w & 0x80000000u) ? ~(int32_t)(a.w & 0x3FFFFFFu) : (int32_t)a.w;
+          rl = (b.w & 0x80000000u) ? ~(int32_t)(b.w & 0x3FFFFFFu) : (int32_t)b.w;
+          lm = ((a.w >> 26) & 31u) + 1u; rm = ((b.w >> 26) & 31u) + 1u;
+        } else {
+          const float4* __restrict__ n = sc.nodes + 4 * (size_t)link;
+          ldg256(n, l0, l1);
+          ldg256(n + 2, r0, r1);
+          ll = __float_as_int(l0.w); rl = __float_as_int(r0.w);
+          lm = __float_as_uint(l1.w); rm = __float_as_uint(r1.w);
+        }
+        if (COUNT) cnt.pairs++;
+        float tl, tr;
+        const bool hl = slab(l0, l1, o, inv, t_min, best_t, tl);
+        const bool hr = slab(r0, r1, o, inv, t_min, best_t, tr);
+        if (hl && hr) {
+          const bool left_first = tl <= tr;
+          stack[sp++] = left_first ? stack_pack(rl, rm) : stack_pack(ll, lm);
+          link = left_first ? ll : rl;
+          meta = left_first ? lm : rm;
+        } else if (hl) {
+          link = ll; meta = lm;
+        } else if (hr) {
+          link = rl; meta = rm;
+        } else if (sp > 0) {
+          stack_unpack(stack[--sp], link, meta);
+        } else {
+          link = RTW_LINK_DONE;
+        }
+      }
+    }
+    // ---- (c) every lane that holds a leaf queues its next primitive ------------------------------------------------------
+    {
+      const bool holder = active && link < 0 && link != RTW_LINK_DONE;
+      const uint32_t m = __ballot_sync(FULL, holder);
+      if (holder) {
+        lp.queue[(tail + __popc(m & lane_lt)) & 63u] = (lane << 27) | (uint32_t)(~link);
+        my_last = tail + __popc(m);
+        link -= 1;  // ~link + 1: the next slot of the leaf
+        meta -= 1;
+        if (meta == 0u) {
+          if (sp > 0) {
+            stack_unpack(stack[--sp], link, meta);
+          } else {
+            link = RTW_LINK_DONE;
+          }
+        }
+      }
+      tail += __popc(m);
+      __syncwarp();
+    }
+    // ---- (d) drain: full batches always; the rest when enough lanes are parked or nothing else can progress -------------
+    {
+      parked = active && link == RTW_LINK_DONE && (int32_t)(head - my_last) < 0;
+      const uint32_t m_parked = __ballot_sync(FULL, parked);
+      const uint32_t m_prog = __ballot_sync(FULL, active && link != RTW_LINK_DONE);
+      const bool force = m_parked != 0u && (__popc(m_parked) >= RTW_POOL_WAIT_LANES || m_prog == 0u);
+      while (tail - head >= 32u || (force && tail != head)) {
+        const uint32_t n = min(tail - head, 32u);
+        const bool v = lane < n;
+        const uint32_t e = v ? lp.queue[(head + lane) & 63u] : 0u;
+        head += n;
+        const uint32_t owner = e >> 27, slot = e & 0x7FFFFFFu;
+        bool hit = false;
+        unsigned long long key = 0ull;
+        if (v) {
+          v3 ro = mk(lp.ray[0][owner], lp.ray[1][owner], lp.ray[2][owner]);
+          v3 rd = mk(lp.ray[3][owner], lp.ray[4][owner], lp.ray[5][owner]);
+          const float rtime = lp.ray[6][owner], rt_min = lp.ray[7][owner];
+          const float bt = ordered_to_float((uint32_t)(lp.best[owner] >> 32));
+          const uint32_t pm = __ldg(sc.slot_meta + slot);
+          const uint32_t type = pm & 7u, inst = pm >> RTW_META_TYPE_BITS;
+          if (inst != 0) ray_to_instance(sc, inst, ro, rd);
+          if (COUNT) {
+            cnt.prims++;
+            cnt.prim_bytes += 4u + ((type == PT_SPHERE) ? 16u : ((type >= PT_RECT_YZ && type <= PT_RECT_XY) ? 32u : 48u));
+          }
+          const float4* __restrict__ g = sc.geom + 3 * (size_t)slot;
+          float t;
+          hit = prim_t(type, g, ro, rd, rtime, rt_min, bt, t);
+          if (hit) {
+            key = ((unsigned long long)float_to_ordered(t) << 32) | (0xFFFFFFFEu - (uint32_t)__ldg(sc.slot_prim + slot));
+            atomicMin(&lp.best[owner], key);
+          }
+        }
+        __syncwarp();
+        if (hit && lp.best[owner] == key) lp.best_slot[owner] = (int32_t)slot;
+        __syncwarp();
+        if (active) best_t = ordered_to_float((uint32_t)(lp.best[lane] >> 32));
+      }
+    }
+    // ---- (e) finished queries -------------------------------------------------------------------------------------------
+    if (active && link == RTW_LINK_DONE && (int32_t)(head - my_last) >= 0) {
+      const int32_t bs = lp.best_slot[lane];
+      io.store(index, o, d, time, bs, ordered_to_float((uint32_t)(lp.best[lane] >> 32)), bs >= 0 ? __ldg(sc.slot_meta + bs) : 0u);
+      active = false;
+    }
+    parked = active && link == RTW_LINK_DONE;  // still waiting for its last entries
   }
 }
 

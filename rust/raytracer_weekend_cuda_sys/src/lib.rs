@@ -1,10 +1,10 @@
-//! `extern "C"` surface of include/rtw_cuda.h (RTW_ABI_VERSION 2), declaration for declaration.
+//! `extern "C"` surface of include/rtw_cuda.h (RTW_ABI_VERSION 3), declaration for declaration.
 //! Every function returns an int: >= 0 on success (ids / counts), < 0 = RTW_ERR_*; the message of the calling
 //! thread's last error is `rtw_last_error()`.
 #![allow(non_camel_case_types)]
 use core::ffi::{c_char, c_int, c_void};
 
-pub const RTW_ABI_VERSION: c_int = 2;
+pub const RTW_ABI_VERSION: c_int = 3;
 pub const RTW_OK: c_int = 0;
 pub const RTW_ERR_INVALID: c_int = -1;
 pub const RTW_ERR_CUDA: c_int = -2;
@@ -106,6 +106,10 @@ pub struct rtw_render_stats {
     pub fused: u32,
     /// devices that rendered the frame
     pub gpus: u32,
+    /// summed CUDA-event time of the ray-reordering passes (if timed)
+    pub ms_sort: f32,
+    /// 1: the rays of every iteration were traced in scene-cell order
+    pub ray_sort: u32,
 }
 
 #[repr(C)]

@@ -542,6 +542,49 @@ def test_million_primitive_scene_uses_compact_pairs_and_matches_brute_force(gpu)
         assert st.node_record_bytes == 32.0 and st.node_visits > st.segments > 160 * 90 * 2
 
 
+@pytest.mark.parametrize("env", ["RTW_RAYSORT", "RTW_POOLED"])
+def test_ray_reordering_and_pooled_leaf_tests_do_not_change_the_frame(gpu, oracle, monkeypatch, env):
+    """world.hit does not depend on the order in which rays are traced (rtw_raysort.cuh: the rays of an iteration sorted
+    by scene cell — on by default for hierarchies beyond the caches) nor on WHO tests a leaf (rtw_traverse.cuh:
+    traverse_pooled, experiment): forced on for small scenes, the frame keeps the oracle's bits, including through the
+    queue-mode tail of the frame (pool smaller than the frame) and with the traversal counters on."""
+    for scene, aspect in (("stress:3000:400", 16 / 9), ("cow-lambert-metal", 16 / 9), ("jumpy-balls", 16 / 9)):
+        with rtw.Scene.from_name(gpu, scene, aspect, seed=3) as sg:
+            cam = sg.cameras[0]
+            frames = {}
+            for value in ("0", "1"):
+                monkeypatch.setenv(env, value)
+                for pool, flags in ((0, 0), (2048, 0), (4096, rtw.RTW_RENDER_COUNT_TRAVERSAL)):
+                    a, st = sg.render(cam, sg.params(96, 54, 6, seed=5, slices=2, pool_size=pool, flags=flags))
+                    if env == "RTW_RAYSORT":
+                        assert st.ray_sort == int(value)
+                    frames[(value, pool, flags)] = (bits(a).copy(), st.segments)
+            ref = frames[("0", 0, 0)]
+            for k, v in frames.items():
+                assert np.array_equal(v[0], ref[0]) and v[1] == ref[1], (scene, env, k)
+        if scene.startswith("stress"):   # solid colours only: the oracle's bits
+            with rtw.Scene.from_name(oracle, scene, aspect, seed=3) as so:
+                ao, sto = so.render(so.cameras[0], so.params(96, 54, 6, seed=5, slices=2))
+                assert np.array_equal(bits(ao), ref[0]) and sto.segments == ref[1]
+
+
+def test_million_primitive_scene_sorts_its_rays_by_default(gpu):
+    """>= 2^20 primitives: compact pairs AND ray reordering are picked by the library itself; RTW_RAYSORT=0 must give the
+    same frame (checked at a size the suite can afford)."""
+    import os
+    with rtw.Scene.from_name(gpu, "stress:200000:100000", 16 / 9, seed=2024) as s:
+        p = s.params(160, 90, 3, seed=3, slices=1)
+        a1, st1 = s.render(s.cameras[0], p)
+        assert st1.ray_sort == 1 and st1.node_record_bytes == 32.0
+        os.environ["RTW_RAYSORT"] = "0"
+        try:
+            a0, st0 = s.render(s.cameras[0], p)
+        finally:
+            del os.environ["RTW_RAYSORT"]
+        assert st0.ray_sort == 0 and st0.segments == st1.segments
+        assert np.array_equal(bits(a0), bits(a1))
+
+
 def test_default_slices_do_not_depend_on_pool_or_partition(gpu):
     """with slices = 0 (auto) the slice count — which fixes the order of the float additions — used to
     follow the pool size and the tile partition, so the bits of a frame changed with the GPU count.  It now follows
