@@ -83,6 +83,7 @@ struct WaveCtl {
   unsigned long long pairs;
   unsigned long long prims;
   unsigned long long prim_bytes;
+  unsigned long long regen_cursor0;  // item cursor before the current iteration's restart demand (k_wave_regen_scan)
   uint32_t count[2];       // entries of the iteration with that parity (identity mode: slot_count)
   uint32_t cursor_traverse;
   uint32_t cursor_shade;
@@ -103,6 +104,9 @@ struct WaveDev {
   WaveCtl* ctl;
   uint32_t slot_count;
   // ray reordering (rtw_raysort.cuh); both null when off
+  uint32_t* restart;         // split shade / restart: per-warp segments of slots whose path ended this iteration
+  uint2* restart_counts;     // per segment: slots that go on with their item (listed from the front), slots that need a new item (from the back)
+  uint32_t* restart_item_base;  // per segment: first work item for its need-an-item slots (k_wave_regen_scan)
   uint32_t* sort_key;     // [slot] key of the ray the slot holds, written with the ray
   const uint32_t* order;  // the entries of the iteration in key order: what the traversal kernel walks
 };
@@ -130,10 +134,11 @@ enum TravKind { TK_PAIR = 0, TK_MEDIA, TK_WIDE, TK_COMPACT, TK_COUNT, TK_COUNT_C
                 TK_POOL_PAIR, TK_POOL_COMPACT, TK_POOL_COUNT_PAIR, TK_POOL_COUNT_COMPACT, TK_N };
 
 struct GraphKey {
-  int kind = -1, batch = 0, grid_t = 0, grid_s = 0, sort = 0;
+  int kind = -1, batch = 0, grid_t = 0, grid_s = 0, sort = 0, split = 0;
   uint32_t pool = 0;
   bool operator==(const GraphKey& o) const {
-    return kind == o.kind && batch == o.batch && grid_t == o.grid_t && grid_s == o.grid_s && pool == o.pool && sort == o.sort;
+    return kind == o.kind && batch == o.batch && grid_t == o.grid_t && grid_s == o.grid_s && pool == o.pool && sort == o.sort &&
+           split == o.split;
   }
 };
 
@@ -156,6 +161,8 @@ struct WaveHost {
   cudaGraphExec_t graph_exec = nullptr;
   int blocks_trav[TK_N] = {};      // persistent grid per TravKind
   int blocks_shade = 0;
+  int blocks_shade_split = 0, blocks_regen = 0;
+  uint32_t restart_pool = 0;       // pool size the restart list was allocated for
   int blocks_mega[2] = {0, 0};  // [LEAN]
 };
 
@@ -518,6 +525,64 @@ __device__ __forceinline__ void regenerate(const FrameDev& f, const WaveDev& w, 
   if (out_queue) queue_push(next_queue, next_count, go, slot);
 }
 
+// ---- sm_100a: the state of a trip arrives through the bulk-copy engine ------------------------------------------------
+// In identity mode (entry i is slot i — all of a frame but its tail) a trip's state is six CONTIGUOUS runs of the pool
+// arrays (32 x 8 B hit records + 5 x 32 x 16 B).  One elected lane asks the copy engine for them (cp.async.bulk,
+// global -> shared, completion counted in bytes on an mbarrier: SASS UBLKCP + SYNCS) as soon as the previous trip's state
+// has been read into registers, so the fetch of trip k+1 overlaps the shading of trip k without holding a single
+// register; the warp then waits on the mbarrier instead of on six scoreboards.  Trips are assigned statically
+// (warp g takes trips g, g + warps, ...): the address of the next trip is known a whole trip ahead, and the per-trip
+// cursor atomic (10 % of the kernel's stall samples in the r02f capture) disappears.  Queue mode (the tail of a frame:
+// scattered slots, few of them) keeps the plain loads and the cursor.
+#ifndef RTW_SHADE_BULK
+#define RTW_SHADE_BULK 1
+#endif
+struct ShadeStage {  // the state of one trip (32 slots), filled by the copy engine
+  float4 ray_o[32], ray_d[32], thr[32], sum[32];
+  uint4 state[32];
+  int2 hit[32];
+};
+constexpr uint32_t kShadeStageBytes = 5u * 512u + 256u;
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "RTW_MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra RTW_MBAR_DONE;\n"
+      "bra RTW_MBAR_WAIT;\n"
+      "RTW_MBAR_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// one lane: fetch the state of the 32 slots from `base` on
+__device__ __forceinline__ void shade_stage_fetch(const WaveDev& w, uint32_t base, ShadeStage& stg, uint64_t* bar) {
+  mbar_expect_tx(bar, kShadeStageBytes);
+  bulk_g2s(stg.ray_o, w.ray_o + base, 512u, bar);
+  bulk_g2s(stg.ray_d, w.ray_d + base, 512u, bar);
+  bulk_g2s(stg.thr, w.thr + base, 512u, bar);
+  bulk_g2s(stg.sum, w.sum + base, 512u, bar);
+  bulk_g2s(stg.state, w.state + base, 512u, bar);
+  bulk_g2s(stg.hit, w.hit + base, 256u, bar);
+}
+
+#ifndef RTW_SHADE_BULK_SINGLE
+#define RTW_SHADE_BULK_SINGLE 0  // the bulk-copy staging inside the single shade kernel: r02 A/B cow 13.07 -> 13.76 ms, off
+#endif
 #ifdef RTW_SHADE_MINBLOCKS  // A/B r01: 6 (80 registers) and 7 (72) are 4 % and 11 % slower than the compiler's choice
 __global__ void __launch_bounds__(128, RTW_SHADE_MINBLOCKS) k_wave_shade(
 #else
@@ -526,6 +591,12 @@ __global__ void __launch_bounds__(128) k_wave_shade(
     SceneDev sc, const FrameDev* __restrict__ fp, WaveDev w, uint32_t parity) {
   __shared__ ShadeBacklog backlog[4];
   __shared__ FrameDev f;
+#if RTW_SHADE_BULK_SINGLE
+  __shared__ __align__(128) ShadeStage stages[4];
+  __shared__ __align__(8) uint64_t stage_bar[4];
+  ShadeStage& stg = stages[threadIdx.x >> 5];
+  uint64_t* bar = &stage_bar[threadIdx.x >> 5];
+#endif
   load_frame(f, fp);
   ShadeBacklog& bl = backlog[threadIdx.x >> 5];
   WaveCtl* ctl = w.ctl;
@@ -543,9 +614,27 @@ __global__ void __launch_bounds__(128) k_wave_shade(
   uint32_t new_paths = 0, nseg = 0;
   uint32_t nback = 0;  // warp-uniform: entries waiting on the backlog
   uint32_t grabbed = 0;
+#if RTW_SHADE_BULK_SINGLE
+  const bool ident = queue == nullptr && (count & 31u) == 0u;  // kernel-uniform: whole trips of consecutive slots
+  uint32_t trip = blockIdx.x * 4u + (threadIdx.x >> 5);         // static assignment: trips trip, trip + warps, ...
+  const uint32_t trip_stride = gridDim.x * 4u;
+  const uint32_t ntrips = count >> 5;
+  uint32_t phase = 0;
+  if (ident) {
+    if (lane == 0) {
+      mbar_init(bar, 1u);
+      if (trip < ntrips) shade_stage_fetch(w, trip << 5, stg, bar);
+    }
+    __syncwarp();
+  } else
+#else
+  const bool ident = false;
+  uint32_t trip = 0;
+  const uint32_t ntrips = 0;
+#endif
   if (lane == 0) grabbed = atomicAdd(&ctl->cursor_shade, 32u);
   for (;;) {
-    const uint32_t base = __shfl_sync(0xffffffffu, grabbed, 0);
+    const uint32_t base = ident ? (trip < ntrips ? trip << 5 : count) : __shfl_sync(0xffffffffu, grabbed, 0);
     const bool more = base < count;  // warp-uniform: another trip of 32 entries
     if (!more && nback == 0) break;
     const uint32_t i = base + lane;
@@ -558,6 +647,23 @@ __global__ void __launch_bounds__(128) k_wave_shade(
     float4 o4, d4, T4, s4;
     int2 h;
     uint4 st;
+#if RTW_SHADE_BULK_SINGLE
+    if (ident && more) {  // the copy engine has (or will have) put this trip's state in shared memory
+      mbar_wait(bar, phase);
+      phase ^= 1u;
+      slot = i;
+      h = stg.hit[lane];
+      o4 = stg.ray_o[lane]; d4 = stg.ray_d[lane];
+      T4 = stg.thr[lane];
+      st = stg.state[lane];
+      s4 = stg.sum[lane];
+      __syncwarp();  // every lane has read the stage: it may be overwritten
+      trip += trip_stride;
+      if (lane == 0 && trip < ntrips) shade_stage_fetch(w, trip << 5, stg, bar);  // overlaps the shading below
+      alive = d4.w == RTW_SLOT_PENDING;
+      active = d4.w == 0.f;
+    } else
+#endif
     if (active) {  // every load of the slot's state is issued before the first use
       slot = queue ? queue[i] : i;
       h = w.hit[slot];
@@ -617,7 +723,7 @@ __global__ void __launch_bounds__(128) k_wave_shade(
     }
     nback += __popc(m_end);
     __syncwarp();
-    if (more && lane == 0) grabbed = atomicAdd(&ctl->cursor_shade, 32u);
+    if (!ident && more && lane == 0) grabbed = atomicAdd(&ctl->cursor_shade, 32u);
     // restart 32 waiting paths together — or, once the entries have run out, whatever is left (ONE call site: the
     // restart code is a fifth of the kernel)
     if (nback >= 32u || !more) {
@@ -632,6 +738,255 @@ __global__ void __launch_bounds__(128) k_wave_shade(
   }
   if (lane == 0 && new_paths) atomicAdd(&ctl->paths, (unsigned long long)new_paths);
   if (lane == 0 && nseg) atomicAdd(&ctl->segments, (unsigned long long)nseg);  // one world.hit per live entry (lib.rs:102)
+}
+
+// ---- shade and restart as TWO kernels (experiment, RTW_SHADE_SPLIT=1) ---------------------------------------------------------------
+// k_wave_shade above is 65 KB of SASS; the r02 captures show its warps waiting for INSTRUCTIONS (no_instruction 1.5-5.4
+// warps per issue: 20 warps per SM in different corners of a kernel twice the size of the instruction cache) as much as
+// for data.  A fifth of that code restarts ended paths (work-item decode, Philox, camera ray) and runs for the 15-25 % of
+// the lanes whose path just ended.  Here it is a kernel of its own:
+//   k_wave_shade_split   shades the iteration's entries.  A path that ends adds its radiance to the slot's running sum
+//                        (or publishes the finished item) and appends its slot to the warp's PRIVATE segment of the
+//                        restart list — no atomics, the count of a segment is written once when the warp leaves.  Trips
+//                        are assigned statically (warp g: trips g, g + warps, ...), so a segment cannot overflow and, in
+//                        identity mode, the copy engine can fetch the next trip's state while this one is shaded.
+//   k_wave_regen         warp g walks segment g 32 entries at a time, all lanes busy: next sample of the slot's item or a
+//                        new item from the cursor (lib.rs:78-88), camera ray (camera.rs:66-74), fresh throughput.
+// Same functions, same per-slot order of the float additions: the frame keeps its bits (RTW_SHADE_SPLIT=0: A/B and
+// parity against the single kernel).
+__device__ __forceinline__ uint32_t restart_segment_capacity(uint32_t slot_count, uint32_t warps) {
+  const uint32_t ntrips = (slot_count + 31u) >> 5;
+  return ((ntrips + warps - 1u) / warps) << 5;
+}
+
+#ifdef RTW_SHADE_MINBLOCKS
+__global__ void __launch_bounds__(128, RTW_SHADE_MINBLOCKS) k_wave_shade_split(
+#else
+__global__ void __launch_bounds__(128) k_wave_shade_split(
+#endif
+    SceneDev sc, const FrameDev* __restrict__ fp, WaveDev w, uint32_t parity) {
+  __shared__ FrameDev f;
+#if RTW_SHADE_BULK
+  __shared__ __align__(128) ShadeStage stages[4];
+  __shared__ __align__(8) uint64_t stage_bar[4];
+  ShadeStage& stg = stages[threadIdx.x >> 5];
+  uint64_t* bar = &stage_bar[threadIdx.x >> 5];
+#endif
+  load_frame(f, fp);
+  WaveCtl* ctl = w.ctl;
+  const uint32_t count = ctl->count[parity];
+  const uint32_t* __restrict__ queue = ctl->qmode[parity] ? w.queue[parity] : nullptr;  // nullptr: identity
+  const bool out_queue = ctl->qmode[parity ^ 1] != 0;
+  uint32_t* next_queue = w.queue[parity ^ 1];
+  uint32_t* next_count = &ctl->count[parity ^ 1];
+  if (blockIdx.x == 0 && threadIdx.x == 0) ctl->cursor_traverse = 0;  // for the next traversal launch
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t lane_lt = (1u << lane) - 1u;
+  const uint64_t seed = ((uint64_t)f.seed_hi << 32) | f.seed_lo;
+  const uint32_t max_depth = f.max_depth;
+  const GlobalInst iv{sc.inst_range, sc.inst_ops};
+  const uint32_t warps = gridDim.x * 4u, warp_g = blockIdx.x * 4u + (threadIdx.x >> 5);
+  uint32_t* __restrict__ segment = w.restart + (size_t)warp_g * restart_segment_capacity(w.slot_count, warps);
+  const uint32_t seg_cap = restart_segment_capacity(w.slot_count, warps);
+  uint32_t n_same = 0, n_need = 0;  // warp-uniform: entries of this warp's segment, from the front / from the back
+  uint32_t nseg = 0;
+  const uint32_t ntrips = (count + 31u) >> 5;
+  uint32_t trip = warp_g;
+#if RTW_SHADE_BULK
+  const bool ident = queue == nullptr && (count & 31u) == 0u;  // kernel-uniform: whole trips of consecutive slots
+  uint32_t phase = 0;
+  if (ident) {
+    if (lane == 0) {
+      mbar_init(bar, 1u);
+      if (trip < ntrips) shade_stage_fetch(w, trip << 5, stg, bar);
+    }
+    __syncwarp();
+  }
+#else
+  const bool ident = false;
+#endif
+  for (; trip < ntrips; trip += warps) {
+    const uint32_t i = (trip << 5) + lane;
+    bool active = i < count;
+    uint32_t slot = 0;
+    bool alive = false;  // slot continues into the next iteration
+    bool ended = false;  // the path ended: the slot goes on the restart list
+    float4 o4, d4, T4, s4;
+    int2 h;
+    uint4 st;
+#if RTW_SHADE_BULK
+    if (ident) {  // the copy engine has (or will have) put this trip's state in shared memory
+      mbar_wait(bar, phase);
+      phase ^= 1u;
+      slot = i;
+      h = stg.hit[lane];
+      o4 = stg.ray_o[lane]; d4 = stg.ray_d[lane];
+      T4 = stg.thr[lane];
+      st = stg.state[lane];
+      s4 = stg.sum[lane];
+      __syncwarp();  // every lane has read the stage: it may be overwritten
+      if (lane == 0 && trip + warps < ntrips) shade_stage_fetch(w, (trip + warps) << 5, stg, bar);  // overlaps the shading below
+      alive = d4.w == RTW_SLOT_PENDING;
+      active = d4.w == 0.f;
+    } else
+#endif
+    if (active) {  // every load of the slot's state is issued before the first use
+      slot = queue ? queue[i] : i;
+      h = w.hit[slot];
+      o4 = w.ray_o[slot]; d4 = w.ray_d[slot];
+      T4 = w.thr[slot];
+      st = w.state[slot];
+      s4 = w.sum[slot];
+      alive = d4.w == RTW_SLOT_PENDING;  // traversal not finished: carried to the next iteration unshaded
+      active = d4.w == 0.f;              // RTW_SLOT_DEAD: identity mode at the end of the frame
+    }
+    if (active) {
+      nseg++;
+      v3 T = mk(T4.x, T4.y, T4.z);
+      uint32_t bounce = st.w & 0xffu;
+      v3 L = mk(0.f, 0.f, 0.f);
+      if (h.x < 0) {  // lib.rs:102-105: miss -> background
+        L = T * f.background;
+        ended = true;
+      } else {
+        const uint32_t meta = sc.slot_meta[h.x];
+        const int2 ms = sc.slot_ms[h.x];
+        const MaterialRec m = sc.materials[ms.x];
+        const uint32_t type = meta & 7u;
+        const float4* __restrict__ g = sc.geom + 3 * (size_t)h.x;
+        const float4 g0 = __ldg(g);
+        float4 g1 = make_float4(0.f, 0.f, 0.f, 0.f), g2 = g1;
+        if (type == PT_MSPHERE || type == PT_TRI) { g1 = __ldg(g + 1); g2 = __ldg(g + 2); }
+        v3 o = mk(o4.x, o4.y, o4.z), d = mk(d4.x, d4.y, d4.z);
+        ended = shade_hit(sc, iv, max_depth, meta, m, ms.y, g0, g1, g2, __int_as_float(h.y), seed, st.x, st.y, o, d, o4.w, T,
+                          bounce, L);
+        if (!ended) {
+          w.ray_o[slot] = make_float4(o.x, o.y, o.z, o4.w);
+          w.ray_d[slot] = make_float4(d.x, d.y, d.z, 0.f);
+          w.thr[slot] = make_float4(T.x, T.y, T.z, 0.f);
+          w.state[slot] = make_uint4(st.x, st.y, st.z, (st.w & ~0xffu) | bounce);
+          if (w.sort_key) w.sort_key[slot] = ray_sort_key(f.sort, o, d);
+          alive = true;
+        }
+      }
+      if (ended) {
+        const v3 sum = mk(s4.x, s4.y, s4.z) + L;  // lib.rs:87: pixel_color += sample_ray(..)
+        if (st.y + 1 < st.z) w.sum[slot] = make_float4(sum.x, sum.y, sum.z, 0.f);  // the item has samples left
+        else publish_item(f, w.partial, st.x, st.w >> 8, sum);                      // item done: its slice sum
+      }
+    }
+    if (out_queue) queue_push(next_queue, next_count, alive, slot);
+    // the slot restarts: with the next sample of its item (front of the segment) or with a new item (back)
+    const bool need = ended && !(st.y + 1 < st.z);
+    const uint32_t m_same = __ballot_sync(0xffffffffu, ended && !need), m_need = __ballot_sync(0xffffffffu, need);
+    if (ended) {
+      if (need) segment[seg_cap - 1u - (n_need + __popc(m_need & lane_lt))] = slot;
+      else segment[n_same + __popc(m_same & lane_lt)] = slot;
+    }
+    n_same += __popc(m_same);
+    n_need += __popc(m_need);
+  }
+  if (lane == 0) w.restart_counts[warp_g] = make_uint2(n_same, n_need);
+  for (int off = 16; off > 0; off >>= 1) nseg += __shfl_xor_sync(0xffffffffu, nseg, off);
+  if (lane == 0 && nseg) atomicAdd(&ctl->segments, (unsigned long long)nseg);  // one world.hit per live entry (lib.rs:102)
+}
+
+// Work items for the slots that finished theirs: one block turns the per-segment demand into item ranges (exclusive
+// scan from the item cursor) — the restart kernel then needs no atomic at all.  (r02: 52 k warp-level atomicAdds on the one
+// 64-bit cursor per iteration were the floor of the restart work: ~5 ns each at the L2, 0.26 ms.)
+__global__ void __launch_bounds__(1024) k_wave_regen_scan(const FrameDev* __restrict__ fp, WaveDev w, uint32_t shade_warps) {
+  __shared__ uint32_t warp_sums[32];
+  const uint32_t per = (shade_warps + 1023u) / 1024u;
+  const uint32_t begin = min(shade_warps, threadIdx.x * per), end = min(shade_warps, begin + per);
+  uint32_t sum = 0;
+  for (uint32_t g = begin; g < end; ++g) sum += w.restart_counts[g].y;
+  uint32_t x = sum;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int off = 1; off < 32; off <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, x, off);
+    if (lane >= (uint32_t)off) x += y;
+  }
+  if (lane == 31) warp_sums[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t v = warp_sums[lane];
+    uint32_t ws = v;
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, ws, off);
+      if (lane >= (uint32_t)off) ws += y;
+    }
+    warp_sums[lane] = ws - v;
+    if (lane == 31) {  // the block's total: advance the cursor (no other kernel touches it while this one runs)
+      const unsigned long long cur = w.ctl->item_cursor;
+      if (cur + ws > fp->n_items) w.ctl->exhausted = 1u;  // ran dry (the cursor may overshoot; harmless): later iterations compact
+      w.ctl->regen_cursor0 = cur;
+      w.ctl->item_cursor = cur + ws;
+    }
+  }
+  __syncthreads();
+  uint32_t run = warp_sums[warp] + (x - sum);
+  for (uint32_t g = begin; g < end; ++g) {
+    w.restart_item_base[g] = run;  // relative to regen_cursor0
+    run += w.restart_counts[g].y;
+  }
+}
+
+// restart the slots the shade kernel listed (lib.rs:83-88).  Work unit = (segment g, batch b of 32 entries), b-major: the
+// non-empty batches of all segments spread evenly over every warp of the grid.
+__global__ void __launch_bounds__(128) k_wave_regen(SceneDev sc, const FrameDev* __restrict__ fp, WaveDev w, uint32_t parity,
+                                                     uint32_t shade_warps) {
+  __shared__ FrameDev f;
+  load_frame(f, fp);
+  WaveCtl* ctl = w.ctl;
+  const bool out_queue = ctl->qmode[parity ^ 1] != 0;
+  uint32_t* next_queue = w.queue[parity ^ 1];
+  uint32_t* next_count = &ctl->count[parity ^ 1];
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warps = gridDim.x * 4u;
+  const uint32_t cap = restart_segment_capacity(w.slot_count, shade_warps);
+  const unsigned long long cursor0 = ctl->regen_cursor0;  // the item cursor before this iteration's demand was added
+  uint32_t new_paths = 0;
+  const uint32_t units = shade_warps * (cap >> 5);
+  for (uint32_t u = blockIdx.x * 4u + (threadIdx.x >> 5); u < units; u += warps) {
+    const uint32_t g = u % shade_warps, base = (u / shade_warps) << 5;
+    const uint2 n = w.restart_counts[g];
+    if (base >= n.x && base + 32u <= cap - n.y) continue;  // this batch holds no entry
+    const uint32_t e = base + lane;
+    const bool same = e < n.x, need = e >= cap - n.y;
+    uint32_t slot = 0;
+    Item it;
+    it.pixel = it.sample = it.sample_end = it.slice = 0;
+    bool go = false;
+    if (same || need) slot = (w.restart + (size_t)g * cap)[e];
+    if (same) {
+      const uint4 st = w.state[slot];
+      it.pixel = st.x; it.sample = st.y + 1; it.sample_end = st.z; it.slice = st.w >> 8;
+      go = true;
+    }
+    bool got = false, retry = false;
+    if (need) {
+      const unsigned long long item = cursor0 + w.restart_item_base[g] + (cap - 1u - e);
+      if (item < f.n_items) {
+        got = decode_item(f, (uint32_t)item, it);
+        retry = !got;  // an item of the tile padding (outside the image): nothing to render, take another one
+      }
+    }
+    if (__any_sync(0xffffffffu, retry)) got = fetch_item(f, ctl, retry, it) || got;  // rare: through the cursor
+    if (got) {
+      w.sum[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+      go = true;
+    }
+    if (go) {
+      start_path(f, w, slot, it);
+      new_paths++;
+    } else if (need) {
+      w.ray_d[slot] = make_float4(0.f, 0.f, 0.f, RTW_SLOT_DEAD);  // no work left for this slot
+      if (w.sort_key) w.sort_key[slot] = RTW_RAYSORT_DEAD_KEY;
+    }
+    if (out_queue) queue_push(next_queue, next_count, go, slot);
+  }
+  for (int off = 16; off > 0; off >>= 1) new_paths += __shfl_xor_sync(0xffffffffu, new_paths, off);
+  if (lane == 0 && new_paths) atomicAdd(&ctl->paths, (unsigned long long)new_paths);
 }
 
 // ---- the fused kernel of one-leaf scenes ------------------------------------------------------------------------------
@@ -820,6 +1175,7 @@ void release_pool(WaveHost* wh) {
   wh->pool = 0;
   wh->rsort = RaySortDev{};
   wh->rsort_pool = 0;
+  wh->restart_pool = 0;
   float4* keep = wh->dev.partial;
   WaveCtl* ctl = wh->dev.ctl;
   wh->dev = WaveDev{};
@@ -875,6 +1231,10 @@ int create_wave(rtw_scene* s, WaveHost** out) {
   }
   RTW_WAVE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wave_shade, 128, 0));
   wh->blocks_shade = std::max(nb, 1) * s->num_sms;
+  RTW_WAVE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wave_shade_split, 128, 0));
+  wh->blocks_shade_split = std::max(nb, 1) * s->num_sms;
+  RTW_WAVE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_wave_regen, 128, 0));
+  wh->blocks_regen = std::max(nb, 1) * s->num_sms;
   RTW_WAVE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_mega_flat<false>, 128, 0));
   wh->blocks_mega[0] = std::max(nb, 1) * s->num_sms;
   RTW_WAVE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_mega_flat<true>, 128, 0));
@@ -1039,6 +1399,22 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
     }
     wh->rsort_pool = wh->pool;
   }
+  // shade and restart as two kernels (k_wave_shade_split + k_wave_regen); RTW_SHADE_SPLIT=0: the single kernel
+  // (r02 A/B, profiles/r02_sweeps.txt: the split kernels lose 8-20 % against the single kernel — the restart code is 40 % of the
+  // shading instructions and gains nothing from running apart — so the single kernel stays the product path)
+  bool split = false;
+  if (const char* e = getenv("RTW_SHADE_SPLIT")) split = !mega && atoi(e) != 0;
+  if (split && wh->restart_pool < wh->pool) {
+    drop_graph(wh);
+    int rc;
+    if ((rc = wave_alloc(&wh->pool_allocs, &wh->dev.restart, (size_t)wh->pool + 32u * 4u * (size_t)wh->blocks_shade_split + 32u)) ||
+        (rc = wave_alloc(&wh->pool_allocs, &wh->dev.restart_counts, 4u * (size_t)wh->blocks_shade_split)) ||
+        (rc = wave_alloc(&wh->pool_allocs, &wh->dev.restart_item_base, 4u * (size_t)wh->blocks_shade_split))) {
+      release_pool(wh);
+      return rc;
+    }
+    wh->restart_pool = wh->pool;
+  }
   wh->dev.sort_key = raysort ? wh->rsort.key : nullptr;
   wh->dev.order = raysort ? wh->rsort.vals[(RTW_RAYSORT_PASSES - 1) & 1] : nullptr;
   f.sort.enabled = raysort ? 1u : 0u;
@@ -1116,7 +1492,17 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
       else k_raysort_scatter<false, false><<<g, RTW_RAYSORT_THREADS, 0, st>>>(cnt, qm, nullptr, kin, vin, r.keys[ps & 1], r.vals[ps & 1], shift, r.hist, r.totals);
     }
   };
-  const uint32_t sort_launches = raysort ? 3u * RTW_RAYSORT_PASSES : 0u;
+  const uint32_t sort_launches = (raysort ? 3u * RTW_RAYSORT_PASSES : 0u) + (split ? 2u : 0u);  // per iteration, on top of traverse + shade
+  auto launch_shade = [&](uint32_t parity, int grid) {
+    if (split) {
+      const int gs = std::min(grid, wh->blocks_shade_split);
+      k_wave_shade_split<<<gs, 128, 0, st>>>(s->dev, dfp, w, parity);
+      k_wave_regen_scan<<<1, 1024, 0, st>>>(dfp, w, (uint32_t)gs * 4u);
+      k_wave_regen<<<wh->blocks_regen, 128, 0, st>>>(s->dev, dfp, w, parity, (uint32_t)gs * 4u);
+    } else {
+      k_wave_shade<<<std::min(grid, wh->blocks_shade), 128, 0, st>>>(s->dev, dfp, w, parity);
+    }
+  };
 
   // All work runs on an internal stream ordered after the caller's stream; the call returns only after that stream has
   // drained, so the caller's stream order is preserved on both sides.
@@ -1158,7 +1544,8 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
       // a small pool does not need the full persistent grid: fewer blocks launch (and drain) faster
       const int need_blocks = (int)((pool + 127u) / 128u);
       key.grid_t = std::min(wh->blocks_trav[kind], std::max(need_blocks, 1));
-      key.grid_s = std::min(wh->blocks_shade, std::max(need_blocks, 1));
+      key.grid_s = std::min(split ? wh->blocks_shade_split : wh->blocks_shade, std::max(need_blocks, 1));
+      key.split = split ? 1 : 0;
       key.pool = pool;
       key.sort = raysort ? 1 : 0;
       if (!(wh->graph_exec && wh->graph_key == key)) {
@@ -1168,7 +1555,7 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
         for (int b = 0; b < key.batch; ++b) {
           if (raysort) launch_sort((uint32_t)(b & 1));
           launch_traverse((uint32_t)(b & 1), key.grid_t);
-          k_wave_shade<<<key.grid_s, 128, 0, st>>>(s->dev, dfp, w, (uint32_t)(b & 1));
+          launch_shade((uint32_t)(b & 1), key.grid_s);
         }
         cudaError_t ce = cudaStreamEndCapture(st, &graph);  // always ends the capture, whatever happened inside
         if (ce == cudaSuccess && fault && !strcmp(fault, "capture")) ce = cudaErrorUnknown;
@@ -1225,7 +1612,7 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
             RTW_CUDA_TRY(cudaEventRecord(e4[1], st));
             RTW_CUDA_TRY(cudaEventRecord(e4[2], st));
           }
-          k_wave_shade<<<wh->blocks_shade, 128, 0, st>>>(s->dev, dfp, w, parity);
+          launch_shade(parity, split ? wh->blocks_shade_split : wh->blocks_shade);
           if (time_kernels) RTW_CUDA_TRY(cudaEventRecord(e4[3], st));
           parity ^= 1;
           launches += 2 + sort_launches;
