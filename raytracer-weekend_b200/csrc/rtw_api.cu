@@ -105,9 +105,10 @@ int rtw_scene_destroy(rtw_scene* s) {
   if (s->built || s->wave) {
     free_replicas(s);
     cudaSetDevice(s->device);
+    cudaDeviceSynchronize();  // (cudaFree used to imply this) the scene's blocks go back to the cache of rtw_mem.cu
     free_wave(s);
     free_scene_device(s);
-    if (s->io_frame) cudaFree(s->io_frame);
+    if (s->io_frame) mem_free(s->io_frame);
   }
   delete s;
   return RTW_OK;
@@ -432,9 +433,8 @@ int rtw_build(rtw_scene* s, float time0, float time1, rtw_build_stats* stats) {
   }
   if (s->device >= ndev) return set_error(RTW_ERR_INVALID, "build: device index out of range");
   RTW_CUDA_TRY(cudaSetDevice(s->device));
-  cudaDeviceProp prop;
-  RTW_CUDA_TRY(cudaGetDeviceProperties(&prop, s->device));
-  s->num_sms = prop.multiProcessorCount;
+  // (one attribute, not cudaGetDeviceProperties: that call takes 30-120 ms on this pool's boxes — tools/e2e_probe.py)
+  RTW_CUDA_TRY(cudaDeviceGetAttribute(&s->num_sms, cudaDevAttrMultiProcessorCount, s->device));
   int rc = build_scene_device(s, time0, time1, stats);
   if (rc != RTW_OK) {
     free_scene_device(s);
@@ -509,11 +509,11 @@ int rtw_trace_closest(rtw_scene* s, const rtw_ray* rays, uint64_t n, rtw_hit* hi
   RTW_CUDA_TRY(cudaSetDevice(s->device));
   rtw_ray* d_rays = nullptr;
   rtw_hit* d_hits = nullptr;
-  cudaError_t e = cudaMalloc((void**)&d_rays, n * sizeof(rtw_ray));
-  if (e == cudaSuccess) e = cudaMalloc((void**)&d_hits, n * sizeof(rtw_hit));
+  cudaError_t e = dev_malloc((void**)&d_rays, n * sizeof(rtw_ray));
+  if (e == cudaSuccess) e = dev_malloc((void**)&d_hits, n * sizeof(rtw_hit));
   if (e != cudaSuccess) {
     cudaGetLastError();
-    cudaFree(d_rays);
+    mem_free(d_rays);
     return set_error(RTW_ERR_NOMEM, "trace: cudaMalloc failed");
   }
   int rc = RTW_OK;
@@ -522,8 +522,8 @@ int rtw_trace_closest(rtw_scene* s, const rtw_ray* rays, uint64_t n, rtw_hit* hi
     rc = trace_closest_device(s, d_rays, n, d_hits, mode, 0);
     if (rc == RTW_OK) e = cudaMemcpy(hits, d_hits, n * sizeof(rtw_hit), cudaMemcpyDeviceToHost);
   }
-  cudaFree(d_rays);
-  cudaFree(d_hits);
+  mem_free(d_rays);
+  mem_free(d_hits);
   if (e != cudaSuccess) return cuda_fail(e, "rtw_trace_closest copy");
   return rc;
 }
@@ -542,10 +542,10 @@ int rtw_render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_para
 // the frame buffer on the scene's device: kept on the scene, grow only
 static int ensure_io(rtw_scene* s, size_t bytes) {
   if (s->io_bytes >= bytes) return RTW_OK;
-  if (s->io_frame) cudaFree(s->io_frame);
+  if (s->io_frame) mem_free(s->io_frame);
   s->io_frame = nullptr;
   s->io_bytes = 0;
-  cudaError_t e = cudaMalloc((void**)&s->io_frame, bytes);
+  cudaError_t e = dev_malloc((void**)&s->io_frame, bytes);
   if (e != cudaSuccess) {
     cudaGetLastError();
     return set_error(RTW_ERR_NOMEM, std::string("render: frame buffer allocation failed: ") + cudaGetErrorString(e));
@@ -594,16 +594,16 @@ int rtw_render_frames(rtw_scene* s, const rtw_camera* cameras, uint32_t n_frames
     for (auto& f : pending)
       if (f.valid()) f.wait();
     for (int b = 0; b < 2; ++b) {
-      cudaFree(d_accum[b]);
-      if (h_accum[b]) cudaFreeHost(h_accum[b]);
+      mem_free(d_accum[b]);
+      if (h_accum[b]) mem_free(h_accum[b]);
       if (copied[b]) cudaEventDestroy(copied[b]);
     }
     if (copy_stream) cudaStreamDestroy(copy_stream);
   };
   cudaError_t e = cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking);
   for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
-    e = cudaMalloc((void**)&d_accum[b], bytes);
-    if (e == cudaSuccess && on_frame) e = cudaMallocHost((void**)&h_accum[b], bytes);
+    e = dev_malloc((void**)&d_accum[b], bytes);
+    if (e == cudaSuccess && on_frame) e = pinned_malloc((void**)&h_accum[b], bytes);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming);
   }
   if (e != cudaSuccess) {
@@ -667,11 +667,11 @@ int rtw_resolve_rgb8(rtw_scene* s, const float* accum_rgb, uint32_t width, uint3
   size_t n = (size_t)width * height * 3;
   float* d_in = nullptr;
   uint8_t* d_out = nullptr;
-  cudaError_t e = cudaMalloc((void**)&d_in, n * sizeof(float) + 4);
-  if (e == cudaSuccess) e = cudaMalloc((void**)&d_out, n + 4);
+  cudaError_t e = dev_malloc((void**)&d_in, n * sizeof(float) + 4);
+  if (e == cudaSuccess) e = dev_malloc((void**)&d_out, n + 4);
   if (e != cudaSuccess) {
     cudaGetLastError();
-    cudaFree(d_in);
+    mem_free(d_in);
     return set_error(RTW_ERR_NOMEM, "resolve: cudaMalloc failed");
   }
   int rc = RTW_OK;
@@ -680,8 +680,8 @@ int rtw_resolve_rgb8(rtw_scene* s, const float* accum_rgb, uint32_t width, uint3
     rc = resolve_rgb8_device(d_in, n, spp, d_out, 0);
     if (rc == RTW_OK) e = cudaMemcpy(rgb8, d_out, n, cudaMemcpyDeviceToHost);
   }
-  cudaFree(d_in);
-  cudaFree(d_out);
+  mem_free(d_in);
+  mem_free(d_out);
   if (e != cudaSuccess) return cuda_fail(e, "rtw_resolve_rgb8 copy");
   return rc;
 }

@@ -581,7 +581,7 @@ template <class T>
 int dev_alloc(rtw_scene* s, T** out, size_t count) {
   void* p = nullptr;
   size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
-  cudaError_t e = cudaMalloc(&p, bytes);
+  cudaError_t e = dev_malloc(&p, bytes);
   if (e != cudaSuccess) {
     cudaGetLastError();
     return set_error(RTW_ERR_NOMEM, std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
@@ -605,7 +605,7 @@ int dev_upload(rtw_scene* s, P* out, const std::vector<T>& v) {
 }  // namespace
 
 void free_scene_device(rtw_scene* s) {
-  for (void* p : s->allocations) cudaFree(p);
+  for (void* p : s->allocations) mem_free(p);
   s->allocations.clear();
   s->allocation_bytes.clear();
   s->device_bytes = 0;
@@ -673,7 +673,7 @@ int build_scene_device(rtw_scene* s, float time0, float time1, rtw_build_stats* 
   const uint32_t chunk = ((n + sort_blocks - 1) / sort_blocks + SORT_THREADS - 1) / SORT_THREADS * SORT_THREADS;
   std::vector<void*> scratch;
   auto salloc = [&](void** p, size_t bytes) -> int {
-    cudaError_t e = cudaMalloc(p, std::max<size_t>(bytes, 16));
+    cudaError_t e = dev_malloc(p, std::max<size_t>(bytes, 16));
     if (e != cudaSuccess) { cudaGetLastError(); return set_error(RTW_ERR_NOMEM, "cudaMalloc (build scratch) failed"); }
     scratch.push_back(*p);
     return RTW_OK;
@@ -778,7 +778,8 @@ int build_scene_device(rtw_scene* s, float time0, float time1, rtw_build_stats* 
     memcpy(&root_collapsed, &h_root[7], 4);
     d.flat_count = (root_collapsed && n <= 32) ? n : 0u;
   }
-  for (void* p : scratch) cudaFree(p);
+  cudaDeviceSynchronize();  // the blocks go back to the cache (rtw_mem.cu): nothing may still be using them
+  for (void* p : scratch) mem_free(p);
 
   // compact pairs: only worth their decode instructions when the hierarchy lives in HBM (>= 2^20 primitives)
   d.nodes_c = nullptr;

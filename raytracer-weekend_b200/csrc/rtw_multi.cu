@@ -80,13 +80,11 @@ int clone_scene(const rtw_scene* src, int device, rtw_scene** out) {
   };
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) return fail(cuda_fail(e, "cudaSetDevice (clone)"));
-  cudaDeviceProp prop;
-  e = cudaGetDeviceProperties(&prop, device);
-  if (e != cudaSuccess) return fail(cuda_fail(e, "cudaGetDeviceProperties (clone)"));
-  d->num_sms = prop.multiProcessorCount;
+  e = cudaDeviceGetAttribute(&d->num_sms, cudaDevAttrMultiProcessorCount, device);
+  if (e != cudaSuccess) return fail(cuda_fail(e, "cudaDeviceGetAttribute (clone)"));
   for (size_t i = 0; i < src->allocations.size(); ++i) {
     void* p = nullptr;
-    e = cudaMalloc(&p, src->allocation_bytes[i]);
+    e = dev_malloc(&p, src->allocation_bytes[i]);
     if (e != cudaSuccess) {
       cudaGetLastError();
       return fail(set_error(RTW_ERR_NOMEM, std::string("clone: cudaMalloc failed: ") + cudaGetErrorString(e)));
@@ -116,13 +114,13 @@ void free_replicas(rtw_scene* s) {
     cudaSetDevice(r->device);
     free_wave(r);
     free_scene_device(r);
-    if (r->io_frame) cudaFree(r->io_frame);
+    if (r->io_frame) mem_free(r->io_frame);
     delete r;
   }
   s->replicas.clear();
   cudaSetDevice(s->device);
   for (float* p : s->staging)
-    if (p) cudaFree(p);
+    if (p) mem_free(p);
   s->staging.clear();
   s->staging_bytes = 0;
 }
@@ -163,18 +161,18 @@ int render_multi_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_pa
     if (!can) {  // render into the replica's own frame, copy it across, merge the owned tiles
       RTW_CUDA_TRY(cudaSetDevice(r->device));
       if (r->io_bytes < bytes) {
-        if (r->io_frame) cudaFree(r->io_frame);
+        if (r->io_frame) mem_free(r->io_frame);
         r->io_frame = nullptr;
         r->io_bytes = 0;
-        RTW_CUDA_TRY(cudaMalloc((void**)&r->io_frame, bytes));
+        RTW_CUDA_TRY(dev_malloc((void**)&r->io_frame, bytes));
         r->io_bytes = bytes;
       }
       RTW_CUDA_TRY(cudaSetDevice(s->device));
       if (s->staging_bytes < bytes) {
-        for (float*& q : s->staging) { if (q) cudaFree(q); q = nullptr; }
+        for (float*& q : s->staging) { if (q) mem_free(q); q = nullptr; }
         s->staging_bytes = bytes;
       }
-      if (!s->staging[i - 1]) RTW_CUDA_TRY(cudaMalloc((void**)&s->staging[i - 1], s->staging_bytes));
+      if (!s->staging[i - 1]) RTW_CUDA_TRY(dev_malloc((void**)&s->staging[i - 1], s->staging_bytes));
       target[i] = r->io_frame;
       staged[i] = true;
     }

@@ -1149,7 +1149,7 @@ __global__ void k_raysort_check(const uint32_t* __restrict__ count, const uint32
 template <class T>
 int wave_alloc(std::vector<void*>* bag, T** out, size_t count) {
   void* p = nullptr;
-  cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+  cudaError_t e = dev_malloc(&p, std::max<size_t>(count, 1) * sizeof(T));
   if (e != cudaSuccess) {
     cudaGetLastError();
     return set_error(RTW_ERR_NOMEM, std::string("cudaMalloc (wavefront state) failed: ") + cudaGetErrorString(e));
@@ -1170,7 +1170,7 @@ void drop_graph(WaveHost* wh) {
 
 void release_pool(WaveHost* wh) {
   drop_graph(wh);  // the graph bakes the pool pointers
-  for (void* p : wh->pool_allocs) cudaFree(p);
+  for (void* p : wh->pool_allocs) mem_free(p);
   wh->pool_allocs.clear();
   wh->pool = 0;
   wh->rsort = RaySortDev{};
@@ -1186,11 +1186,11 @@ void release_pool(WaveHost* wh) {
 void destroy_wave(WaveHost* wh) {
   if (!wh) return;
   release_pool(wh);
-  if (wh->partial) cudaFree(wh->partial);
-  if (wh->d_ctl) cudaFree(wh->d_ctl);
-  if (wh->d_frame) cudaFree(wh->d_frame);
-  if (wh->h_frame) cudaFreeHost(wh->h_frame);
-  if (wh->pinned_ctl) cudaFreeHost(wh->pinned_ctl);
+  if (wh->partial) mem_free(wh->partial);
+  if (wh->d_ctl) mem_free(wh->d_ctl);
+  if (wh->d_frame) mem_free(wh->d_frame);
+  if (wh->h_frame) mem_free(wh->h_frame);
+  if (wh->pinned_ctl) mem_free(wh->pinned_ctl);
   drop_event(wh->ev_in); drop_event(wh->ev_begin); drop_event(wh->ev_end);
   drop_event(wh->ring_ev[0]); drop_event(wh->ring_ev[1]);
   drop_stream(wh->stream);
@@ -1207,10 +1207,10 @@ int create_wave(rtw_scene* s, WaveHost** out) {
     cudaError_t _e = (expr);                                        \
     if (_e != cudaSuccess) return fail(cuda_fail(_e, #expr));       \
   } while (0)
-  RTW_WAVE_TRY(cudaMallocHost((void**)&wh->pinned_ctl, 3 * sizeof(WaveCtl)));
-  RTW_WAVE_TRY(cudaMallocHost((void**)&wh->h_frame, sizeof(FrameDev)));
-  RTW_WAVE_TRY(cudaMalloc((void**)&wh->d_frame, sizeof(FrameDev)));
-  RTW_WAVE_TRY(cudaMalloc((void**)&wh->d_ctl, sizeof(WaveCtl)));
+  RTW_WAVE_TRY(pinned_malloc((void**)&wh->pinned_ctl, 3 * sizeof(WaveCtl)));
+  RTW_WAVE_TRY(pinned_malloc((void**)&wh->h_frame, sizeof(FrameDev)));
+  RTW_WAVE_TRY(dev_malloc((void**)&wh->d_frame, sizeof(FrameDev)));
+  RTW_WAVE_TRY(dev_malloc((void**)&wh->d_ctl, sizeof(WaveCtl)));
   wh->dev.ctl = wh->d_ctl;
   RTW_WAVE_TRY(new_stream(&wh->stream));
   RTW_WAVE_TRY(new_event(&wh->ev_in, cudaEventDisableTiming));
@@ -1427,7 +1427,7 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
   const size_t partial_elems = slices > 1 ? (size_t)slices * f.pix_per_slice : 0;
   if (wh->partial_elems < partial_elems) {
     drop_graph(wh);
-    if (wh->partial) cudaFree(wh->partial);
+    if (wh->partial) mem_free(wh->partial);
     wh->partial = nullptr;
     wh->partial_elems = 0;
     int rc = wave_alloc((std::vector<void*>*)nullptr, &wh->partial, partial_elems);
@@ -1583,7 +1583,7 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
     } else {
       // ---- instrumented path (traversal counters / per-kernel CUDA events): plain launches
       if (raysort && getenv("RTW_RAYSORT_CHECK")) {
-        cudaMalloc((void**)&d_check, 3 * sizeof(unsigned long long));
+        dev_malloc((void**)&d_check, 3 * sizeof(unsigned long long));
         cudaMemsetAsync(d_check, 0, 3 * sizeof(unsigned long long), st);
       }
       k_wave_init<<<(pool + 127) / 128, 128, 0, st>>>(s->dev, dfp, w);
@@ -1636,7 +1636,7 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
   if (d_check) {
     unsigned long long hc[3] = {0, 0, 0};
     cudaMemcpy(hc, d_check, sizeof(hc), cudaMemcpyDeviceToHost);
-    cudaFree(d_check);
+    mem_free(d_check);
     fprintf(stdout, "[raysort check] inversions %llu, key changes %llu over %llu sorted entries\n", hc[0], hc[1], hc[2]);
   }
   const WaveCtl total = wh->pinned_ctl[2];

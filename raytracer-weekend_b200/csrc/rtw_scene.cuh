@@ -77,6 +77,12 @@ struct rtw_scene {
 
 namespace rtw {
 
+// rtw_mem.cu: device / pinned memory with a process-wide cache of freed blocks (scene, build and render scratch)
+cudaError_t dev_malloc(void** out, size_t bytes);     // on the current device
+cudaError_t pinned_malloc(void** out, size_t bytes);  // page-locked host memory
+void mem_free(void* p);                               // from either of the two; nullptr ignored
+void mem_trim();                                      // give every cached block back to the driver
+
 // rtw_bvh.cu: upload the flattened scene and build the LBVH on the GPU.
 int build_scene_device(rtw_scene* s, float time0, float time1, rtw_build_stats* stats);
 void free_scene_device(rtw_scene* s);

@@ -21,7 +21,7 @@ fn main() {
         .unwrap_or_else(|_| manifest.join("../../raytracer-weekend_b200/csrc"));
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "/usr/local/cuda/bin/nvcc".into());
-    let units = ["rtw_api", "rtw_bvh", "rtw_trace", "rtw_render"];
+    let units = ["rtw_api", "rtw_bvh", "rtw_trace", "rtw_render", "rtw_multi", "rtw_mem"];
     let mut objects = Vec::new();
     for u in units {
         let cu = src.join(format!("{u}.cu"));
@@ -38,7 +38,7 @@ fn main() {
         assert!(status.success(), "nvcc failed on {}", cu.display());
         objects.push(obj);
     }
-    for h in ["rtw_device.cuh", "rtw_scene.cuh", "rtw_traverse.cuh"] {
+    for h in ["rtw_device.cuh", "rtw_scene.cuh", "rtw_traverse.cuh", "rtw_raysort.cuh"] {
         println!("cargo:rerun-if-changed={}", src.join(h).display());
     }
     let lib = out.join("librtw_cuda.so");

@@ -4,7 +4,7 @@ set -e
 N=$1; shift
 cd "$(dirname "$0")/../raytracer-weekend_b200/csrc"
 mkdir -p build_$N ../lib/ab_$N
-for f in rtw_api rtw_bvh rtw_trace rtw_render rtw_multi; do
+for f in rtw_api rtw_bvh rtw_trace rtw_render rtw_multi rtw_mem; do
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -fmad=false -ccbin /usr/bin/g++ \
     -Xcompiler -fPIC,-ffp-contract=off "$@" -c $f.cu -o build_$N/$f.o &
 done
