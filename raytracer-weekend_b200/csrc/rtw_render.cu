@@ -1643,12 +1643,14 @@ int render_device(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* 
   float ms = 0.f;
   cudaEventElapsedTime(&ms, wh->ev_begin, wh->ev_end);
   float ms_t = 0.f, ms_s = 0.f;
+  const bool trace_iterations = getenv("RTW_TRACE_ITERATIONS") != nullptr;  // debug: per-iteration kernel times of the instrumented path
   for (size_t i = 0; i + 3 < kev.v.size(); i += 4) {
     float a = 0.f, b = 0.f;
     cudaEventElapsedTime(&a, kev.v[i], kev.v[i + 1]);
     cudaEventElapsedTime(&b, kev.v[i + 2], kev.v[i + 3]);
     ms_t += a;
     ms_s += b;
+    if (trace_iterations) fprintf(stdout, "[iteration %zu] traverse %.3f ms  shade %.3f ms\n", i / 4, a, b);
   }
   float ms_sort = 0.f;
   for (size_t i = 0; i + 1 < sev.v.size(); i += 2) {
