@@ -577,6 +577,150 @@ __global__ void k_sort_leaf_ranges(uint32_t n_internal, const uint32_t* __restri
   }
 }
 
+// ---- tree rotations (r02) ---------------------------------------------------------------------------------------------
+// A Karras tree splits where the Morton prefix changes: spatial medians.  Measured offline on the trees this file builds
+// (tools/dump_bvh.py + tools/sah_study.py): the expected number of pair visits, sum of SA(internal node) / SA(root), is
+// 1.42x (cow) / 1.54x (monument) / 2.0x (jumpy-balls: one huge sphere next to 485 small ones) that of a full-sweep SAH
+// tree over the same leaves — and ONE bottom-up pass of tree rotations (Kensler 2008) closes almost all of that gap
+// (cow 3.93 -> 2.92 vs 2.78 for the sweep build; monument 14.2 -> 9.9 -> 9.1 vs 9.2; jumpy 2.0 -> 1.0).
+// The pass has the shape of k_refit: one thread per leaf record climbs, the second thread to arrive at a pair owns it, so
+// the whole subtree below is final.  At pair p with children A, B it looks at the (up to) four grandchildren and applies
+// the best of: B <-> A1, B <-> A2, A <-> B1, A <-> B2, A1 <-> B1, A1 <-> B2 — whichever lowers the surface area of the
+// nodes below p most (p's own box does not change).  Only child RECORDS move between pairs; pair indices, leaves (slot
+// ranges) and everything the traversal relies on stay as they are, and closest hits do not depend on the tree's shape.
+// A rotation may make p deeper; the stack of the walk is RTW_STACK_SIZE entries, so a candidate is refused when it would
+// lift p above max(its current height, kRotateHeightCap), and the build falls back to the unrotated tree if the root still
+// ends up too deep.
+constexpr uint32_t kRotateHeightCap = 56;
+
+// live[p]: pair p is part of the final tree (neither it nor an ancestor collapsed into a leaf)
+__global__ void k_rotate_live(uint32_t n_internal, const uint32_t* __restrict__ collapsed, const uint32_t* __restrict__ node_parent,
+                              uint32_t* __restrict__ live) {
+  uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_internal) return;
+  uint32_t ok = collapsed[p] ? 0u : 1u;
+  for (uint32_t q = p; ok && q != 0;) {
+    q = node_parent[q] >> 1;
+    if (collapsed[q]) ok = 0u;
+  }
+  live[p] = ok;
+}
+
+struct ChildRec {
+  float4 lo, hi;  // lo.w = link, hi.w = meta
+};
+__device__ __forceinline__ ChildRec load_rec(const float4* nodes, uint32_t rec) {
+  ChildRec r;
+  r.lo = __ldcg(&nodes[2 * (size_t)rec]);
+  r.hi = __ldcg(&nodes[2 * (size_t)rec + 1]);
+  return r;
+}
+__device__ __forceinline__ void put_rec(float4* nodes, uint32_t* node_parent, uint32_t pair, uint32_t side, const ChildRec& r) {
+  __stcg(&nodes[2 * (size_t)(2 * pair + side)], r.lo);
+  __stcg(&nodes[2 * (size_t)(2 * pair + side) + 1], r.hi);
+  const int32_t link = __float_as_int(r.lo.w);
+  if (link >= 0) node_parent[link] = (pair << 1) | side;
+}
+__device__ __forceinline__ ChildRec union_rec(const ChildRec& a, const ChildRec& b, int32_t link) {
+  ChildRec r;
+  r.lo = make_float4(fminf(a.lo.x, b.lo.x), fminf(a.lo.y, b.lo.y), fminf(a.lo.z, b.lo.z), __int_as_float(link));
+  r.hi = make_float4(fmaxf(a.hi.x, b.hi.x), fmaxf(a.hi.y, b.hi.y), fmaxf(a.hi.z, b.hi.z), __uint_as_float(0u));
+  return r;
+}
+__device__ __forceinline__ float rec_area(const ChildRec& r) {
+  return half_area(mk(r.lo.x, r.lo.y, r.lo.z), mk(r.hi.x, r.hi.y, r.hi.z));
+}
+__device__ __forceinline__ uint32_t rec_height(const ChildRec& r, const uint32_t* heights) {
+  const int32_t link = __float_as_int(r.lo.w);
+  return link >= 0 ? __ldcg(&heights[link]) : 0u;
+}
+
+// start[t]: record t = (pair t / 2, side t % 2) is a leaf record of a live pair NOW — taken before the pass, because the pass
+// itself moves leaf records between pairs
+__global__ void k_rotate_starts(uint32_t n_internal, const uint32_t* __restrict__ live, const float4* __restrict__ nodes,
+                                uint8_t* __restrict__ start) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 2 * n_internal) return;
+  start[t] = (live[t >> 1] && __float_as_int(nodes[2 * (size_t)t].w) < 0) ? 1 : 0;
+}
+
+__global__ void k_rotate(uint32_t n_internal, const uint8_t* __restrict__ start, uint32_t* __restrict__ node_parent,
+                         uint32_t* __restrict__ flags, uint32_t* __restrict__ heights, float4* __restrict__ nodes,
+                         uint32_t* __restrict__ out_info /* [0] root height, [2] rotations applied */) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t p = t >> 1;
+  if (p >= n_internal || !start[t]) return;
+  uint32_t applied = 0;
+  for (;;) {
+    __threadfence();
+    if (atomicAdd(&flags[p], 1u) == 0u) break;  // first to arrive: the sibling subtree's thread will own the pair
+    __threadfence();
+    ChildRec A = load_rec(nodes, 2 * p), B = load_rec(nodes, 2 * p + 1);
+    const int32_t la = __float_as_int(A.lo.w), lb = __float_as_int(B.lo.w);
+    ChildRec A1 = A, A2 = A, B1 = B, B2 = B;
+    uint32_t hA1 = 0, hA2 = 0, hB1 = 0, hB2 = 0;
+    if (la >= 0) { A1 = load_rec(nodes, 2 * (uint32_t)la); A2 = load_rec(nodes, 2 * (uint32_t)la + 1); hA1 = rec_height(A1, heights); hA2 = rec_height(A2, heights); }
+    if (lb >= 0) { B1 = load_rec(nodes, 2 * (uint32_t)lb); B2 = load_rec(nodes, 2 * (uint32_t)lb + 1); hB1 = rec_height(B1, heights); hB2 = rec_height(B2, heights); }
+    const uint32_t hA = la >= 0 ? 1u + max(hA1, hA2) : 0u, hB = lb >= 0 ? 1u + max(hB1, hB2) : 0u;
+    const uint32_t h_cur = 1u + max(hA, hB);
+    const uint32_t h_max = max(h_cur, kRotateHeightCap);
+    const float sA = rec_area(A), sB = rec_area(B);
+    float best = -1e-6f * (sA + sB);  // a rotation must win by more than rounding noise
+    int which = 0;
+    uint32_t h_new = h_cur;
+    auto consider = [&](int id, float delta, uint32_t h) {
+      if (delta < best && h <= h_max) { best = delta; which = id; h_new = h; }
+    };
+    if (la >= 0) {
+      consider(1, rec_area(union_rec(B, A2, 0)) - sA, 1u + max(hA1, 1u + max(hB, hA2)));  // B <-> A1
+      consider(2, rec_area(union_rec(A1, B, 0)) - sA, 1u + max(hA2, 1u + max(hA1, hB)));  // B <-> A2
+    }
+    if (lb >= 0) {
+      consider(3, rec_area(union_rec(A, B2, 0)) - sB, 1u + max(hB1, 1u + max(hA, hB2)));  // A <-> B1
+      consider(4, rec_area(union_rec(B1, A, 0)) - sB, 1u + max(hB2, 1u + max(hB1, hA)));  // A <-> B2
+    }
+    if (la >= 0 && lb >= 0) {
+      consider(5, rec_area(union_rec(B1, A2, 0)) + rec_area(union_rec(A1, B2, 0)) - sA - sB,
+               2u + max(max(hB1, hA2), max(hA1, hB2)));  // A1 <-> B1
+      consider(6, rec_area(union_rec(B2, A2, 0)) + rec_area(union_rec(B1, A1, 0)) - sA - sB,
+               2u + max(max(hB2, hA2), max(hB1, hA1)));  // A1 <-> B2
+    }
+    const uint32_t ua = (uint32_t)la, ub = (uint32_t)lb;
+    switch (which) {
+      case 1: put_rec(nodes, node_parent, ua, 0, B); put_rec(nodes, node_parent, p, 0, union_rec(B, A2, la)); put_rec(nodes, node_parent, p, 1, A1); break;
+      case 2: put_rec(nodes, node_parent, ua, 1, B); put_rec(nodes, node_parent, p, 0, union_rec(A1, B, la)); put_rec(nodes, node_parent, p, 1, A2); break;
+      case 3: put_rec(nodes, node_parent, ub, 0, A); put_rec(nodes, node_parent, p, 1, union_rec(A, B2, lb)); put_rec(nodes, node_parent, p, 0, B1); break;
+      case 4: put_rec(nodes, node_parent, ub, 1, A); put_rec(nodes, node_parent, p, 1, union_rec(B1, A, lb)); put_rec(nodes, node_parent, p, 0, B2); break;
+      case 5:
+        put_rec(nodes, node_parent, ua, 0, B1); put_rec(nodes, node_parent, ub, 0, A1);
+        put_rec(nodes, node_parent, p, 0, union_rec(B1, A2, la)); put_rec(nodes, node_parent, p, 1, union_rec(A1, B2, lb));
+        break;
+      case 6:
+        put_rec(nodes, node_parent, ua, 0, B2); put_rec(nodes, node_parent, ub, 1, A1);
+        put_rec(nodes, node_parent, p, 0, union_rec(B2, A2, la)); put_rec(nodes, node_parent, p, 1, union_rec(B1, A1, lb));
+        break;
+      default: break;
+    }
+    if (which) {
+      applied++;
+      // the heights of the rewritten children (their pairs keep their indices)
+      if (which == 1) heights[ua] = 1u + max(hB, hA2);
+      if (which == 2) heights[ua] = 1u + max(hA1, hB);
+      if (which == 3) heights[ub] = 1u + max(hA, hB2);
+      if (which == 4) heights[ub] = 1u + max(hB1, hA);
+      if (which == 5) { heights[ua] = 1u + max(hB1, hA2); heights[ub] = 1u + max(hA1, hB2); }
+      if (which == 6) { heights[ua] = 1u + max(hB2, hA2); heights[ub] = 1u + max(hB1, hA1); }
+    }
+    heights[p] = h_new;
+    if (p == 0) {
+      out_info[0] = h_new;
+      break;
+    }
+    p = node_parent[p] >> 1;
+  }
+  if (applied) atomicAdd(&out_info[2], applied);
+}
+
 template <class T>
 int dev_alloc(rtw_scene* s, T** out, size_t count) {
   void* p = nullptr;
@@ -700,7 +844,7 @@ int build_scene_device(rtw_scene* s, float time0, float time1, rtw_build_stats* 
   if ((rc = salloc((void**)&d_lparent, 4ull * n))) return rc;
   if ((rc = salloc((void**)&d_flags, 4ull * n))) return rc;
   if ((rc = salloc((void**)&d_heights, 4ull * n))) return rc;
-  if ((rc = salloc((void**)&d_root, 4 * 8))) return rc;
+  if ((rc = salloc((void**)&d_root, 4 * 12))) return rc;  // box (6), height, root collapsed, rotations applied
   d_info = (uint32_t*)(d_root + 6);
 
   const uint32_t T = 256, G = (n + T - 1) / T;
@@ -743,6 +887,37 @@ int build_scene_device(rtw_scene* s, float time0, float time1, rtw_build_stats* 
                     d_nodes, d_root, d_info);
   if (n > 1) k_sort_leaf_ranges<<<G, T>>>(n - 1, d_collapsed, d_nparent, d_nrange, d.prim_meta, d_v0);
   k_emit_leaves<<<G, T>>>(n, d_v0, d_enc, d.prim_meta, d.prim_mat, d.prim_shade, d_geom, d_slot_prim, d_slot_meta, d_slot_ms);
+  // tree rotations: RTW_ROTATE = number of bottom-up passes (default 2, 0 = the plain Karras tree)
+  int rotate_passes = 2;
+  if (const char* e = getenv("RTW_ROTATE")) rotate_passes = std::max(0, std::min(atoi(e), 8));
+  uint32_t rotations = 0;
+  if (n > 2 && rotate_passes > 0 && !rp.force_flat) {
+    uint32_t h_info[4] = {0, 0, 0, 0};
+    RTW_CUDA_TRY(cudaMemcpy(h_info, d_info, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost));  // [0] height, [1] root collapsed
+    if (!h_info[1]) {
+      uint32_t* d_live = (uint32_t*)d_ncost;  // the SAH costs are no longer needed
+      const uint32_t G2 = (2 * (n - 1) + T - 1) / T;
+      k_rotate_live<<<G, T>>>(n - 1, d_collapsed, d_nparent, d_live);
+      RTW_CUDA_TRY(cudaMemset(d_info + 2, 0, sizeof(uint32_t)));
+      uint8_t* d_start = (uint8_t*)d_v1;  // sort scratch (4 n bytes), free since the last radix pass
+      for (int pass = 0; pass < rotate_passes; ++pass) {
+        RTW_CUDA_TRY(cudaMemset(d_flags, 0, 4ull * n));
+        k_rotate_starts<<<G2, T>>>(n - 1, d_live, d_nodes, d_start);
+        k_rotate<<<G2, T>>>(n - 1, d_start, d_nparent, d_flags, d_heights, d_nodes, d_info);
+      }
+      RTW_CUDA_TRY(cudaMemcpy(h_info, d_info, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+      rotations = h_info[2];
+      if (h_info[0] + 2 > RTW_STACK_SIZE) {  // (never seen) too deep for the traversal stack: back to the Karras tree
+        RTW_CUDA_TRY(cudaMemset(d_flags, 0, 4ull * n));
+        RTW_CUDA_TRY(cudaMemset(d_heights, 0, 4ull * n));
+        k_karras<<<G, T>>>((int)n, d_k0, d_nparent, d_lparent, d_nrange);
+        k_refit<<<G, T>>>(n, d_v0, d_lo, d_hi, rp, d_nparent, d_lparent, d_nrange, d_flags, d_heights, d_ncost, d_collapsed,
+                          d_nodes, d_root, d_info);
+        rotations = 0;
+      }
+    }
+  }
+  (void)rotations;
   d.nodes4 = nullptr;
   if (const char* e = getenv("RTW_WIDE")) {  // the 4-wide records exist only for the experiment that reads them
     if (atoi(e) != 0) {
