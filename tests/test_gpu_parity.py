@@ -214,6 +214,45 @@ def test_bvh_structure(gpu):
             assert s.build_stats.num_prims == n and s.build_stats.max_depth < 90
 
 
+def _internal_area(scene):
+    """sum of SA over the internal nodes of the built tree / SA(root): the expected pair visits of a random ray"""
+    nodes, _, root = scene.get_bvh()
+    def area(lo, hi):
+        d = np.maximum(hi.astype(np.float64) - lo.astype(np.float64), 0)
+        return d[0] * d[1] + d[1] * d[2] + d[2] * d[0]
+    total, depth_max, stack = area(root[:3], root[3:]), 0, [(0, 1)]
+    while stack:
+        pair, depth = stack.pop()
+        depth_max = max(depth_max, depth)
+        for rec in nodes[2 * pair:2 * pair + 2]:
+            if rec["link"] >= 0:
+                total += area(rec["bmin"], rec["bmax"])
+                stack.append((int(rec["link"]), depth + 1))
+    return total / area(root[:3], root[3:]), depth_max
+
+
+def test_tree_rotations_lower_the_sah_cost_and_change_no_hit(gpu, oracle, monkeypatch):
+    """rtw_bvh.cu: k_rotate.  The rotated tree has the same leaves and boxes that still contain them (test_bvh_structure runs
+    on it), a clearly lower expected number of pair visits than the plain Karras tree (RTW_ROTATE=0), a depth the
+    traversal stack holds — and the same closest hits and the same frame, bit for bit: world.hit does not depend on the
+    shape of the tree."""
+    for scene, gain in (("cow-lambert-metal", 0.80), ("jumpy-balls", 0.60), ("stress:3000:400", 0.99)):
+        res = {}
+        for passes in ("0", "4"):
+            monkeypatch.setenv("RTW_ROTATE", passes)   # read by rtw_build
+            with rtw.Scene.from_name(gpu, scene, 16 / 9, seed=3) as sg, rtw.Scene.from_name(oracle, scene, 16 / 9, seed=3) as so:
+                cost, depth = _internal_area(sg)
+                assert depth + 2 <= 96 and sg.build_stats.max_depth + 2 <= 96
+                rays = oracle.capture_rays(so, so.cameras[0], 160, 90, 11, 0, 1)
+                hits = sg.trace_closest(rays)
+                a, st = sg.render(sg.cameras[0], sg.params(96, 54, 4, seed=5, slices=2))
+                res[passes] = (cost, hits, bits(a).copy(), st.segments)
+        monkeypatch.delenv("RTW_ROTATE")
+        assert res["4"][0] <= gain * res["0"][0], (scene, res["0"][0], res["4"][0])
+        assert_hits_equal(res["4"][1], res["0"][1], f"rotations {scene}")
+        assert np.array_equal(res["4"][2], res["0"][2]) and res["4"][3] == res["0"][3]
+
+
 def test_resolve_rgb8_matches_reference_tonemap(gpu, oracle):
     rs = np.random.RandomState(0)
     acc = (rs.uniform(0, 3, (64, 48, 3)) ** 3).astype(np.float32) * 16

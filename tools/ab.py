@@ -41,8 +41,8 @@ p = scene.params(w, h, spp, seed=2024, flags=2, pool_size=int(os.environ.get('AB
 for i in range(2):
     st = scene.render_device(cam, p, accum.data_ptr(), stream.cuda_stream)
 torch.cuda.synchronize()
-print('%%-10s %%-16s %%8.1f Mrays/s | single pool: traverse %%8.2f ms  sort %%6.2f ms  shade %%8.2f ms  (%%d iterations, %%.1f Mseg, pool %%d)' %% (
-    %(var)r, %(work)r, best, st.ms_traverse, st.ms_sort, st.ms_shade, st.iterations, st.segments / 1e6, st.pool_size))
+print('%%-10s %%-16s %%8.1f Mrays/s | single pool: traverse %%8.2f ms  sort %%6.2f ms  shade %%8.2f ms  (%%d iterations, %%.1f Mseg, pool %%d, build %%.2f ms, height %%d)' %% (
+    %(var)r, %(work)r, best, st.ms_traverse, st.ms_sort, st.ms_shade, st.iterations, st.segments / 1e6, st.pool_size, scene.build_stats.ms_build, scene.build_stats.max_depth))
 """
 
 
