@@ -26,10 +26,12 @@ except Exception as e:
 P
 )"
 }
-for n in 8 4 2 1; do run $n cornell --steps 3 --warmup 3 --no-cpu-baseline; done
-for n in 8 1; do run $n monument_full --workload monument --steps 2 --warmup 1 --no-cpu-baseline; done
-for n in 8 1; do run $n stress32 --workload stress --spp 32 --steps 2 --warmup 1 --no-cpu-baseline; done
+NS=${1:-"8 4 2 1"}; NF=${2:-"8 1"}   # rank counts for the default line / for the full-size C4 and C5 runs
+for n in $NS; do run $n cornell --steps 3 --warmup 3 --no-cpu-baseline; done
+for n in $NF; do run $n monument_full --workload monument --steps 2 --warmup 1 --no-cpu-baseline; done
+for n in $NF; do run $n stress32 --workload stress --spp 32 --steps 2 --warmup 1 --no-cpu-baseline; done
 # the product's own multi-GPU entry: one process, rtw_render(gpus = 8), peer stores into one frame
-timeout 300 python bench.py --gpus 8 --steps 3 --warmup 2 --no-cpu-baseline --no-per-config > $O/r02_scale_single_process_8.json 2> $O/r02_scale_single_process_8.err
-echo "single process gpus=8 rc=$?"; tail -c 400 $O/r02_scale_single_process_8.json
-timeout 300 python -m pytest tests -m gpu -q -k "gpus or clone or two" 2>&1 | tail -3 | tee $O/r02_scale_multigpu_tests.txt
+NG=$(nvidia-smi -L | wc -l)
+timeout 300 python bench.py --gpus $NG --steps 3 --warmup 2 --no-cpu-baseline --no-per-config > $O/r02_scale_single_process_$NG.json 2> $O/r02_scale_single_process_$NG.err
+echo "single process gpus=$NG rc=$?"; tail -c 400 $O/r02_scale_single_process_$NG.json
+[ -z "${R02_SKIP_TESTS:-}" ] && timeout 300 python -m pytest tests -m gpu -q -k "gpus or clone or two" 2>&1 | tail -3 | tee $O/r02_scale_multigpu_tests.txt
