@@ -160,6 +160,10 @@ int rtw_scene_destroy(rtw_scene *s);
 int rtw_scene_clone(const rtw_scene *src, int device, rtw_scene **out);
 /* events / streams / graphs this library holds right now (0 once every scene is destroyed): leak check for tests */
 int rtw_debug_live_handles(void);
+/* The library keeps freed device and pinned blocks for the next scene (a front end that builds a scene per frame would
+ * otherwise pay tens to hundreds of ms of cudaMalloc / cudaFree per scene).  This gives every cached block back to the
+ * driver; returns the number of bytes released as a count of MiB (>= 0).  RTW_MEM_CACHE=0 disables the cache. */
+int rtw_trim_memory(void);
 
 /* ---- textures: texture.rs, image_texture.rs ---------------------------------------------- */
 int rtw_add_texture_solid(rtw_scene *s, float r, float g, float b);            /* texture.rs:45-60  */

@@ -177,6 +177,10 @@ class Backend:
         """rtw_debug_live_handles: CUDA events / streams / graphs the library holds right now."""
         return int(self.fn("debug_live_handles")())
 
+    def trim_memory(self) -> int:
+        """rtw_trim_memory: give the library's cache of freed device / pinned blocks back to the driver (MiB released)."""
+        return int(self.fn("trim_memory")())
+
     def new_scene(self, device: int = 0) -> "Scene":
         return Scene(self, device)
 

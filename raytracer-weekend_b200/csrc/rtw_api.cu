@@ -125,6 +125,8 @@ int rtw_scene_clone(const rtw_scene* src, int device, rtw_scene** out) {
 
 int rtw_debug_live_handles(void) { return live_handles(); }
 
+int rtw_trim_memory(void) { return (int)(mem_trim() >> 20); }
+
 // ---- textures ----------------------------------------------------------------------------------
 int rtw_add_texture_solid(rtw_scene* s, float r, float g, float b) {
   CHECK_OPEN(s);

@@ -135,9 +135,11 @@ void mem_free(void* p) {
   if (b.device >= 0 && b.device != cur) cudaSetDevice(cur);
 }
 
-void mem_trim() {
+size_t mem_trim() {
   std::lock_guard<std::mutex> lk(g_mu);
+  const size_t released = g_cached_bytes;
   drop_cache_locked();
+  return released;
 }
 
 }  // namespace rtw

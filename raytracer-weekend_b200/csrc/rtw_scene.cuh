@@ -81,7 +81,7 @@ namespace rtw {
 cudaError_t dev_malloc(void** out, size_t bytes);     // on the current device
 cudaError_t pinned_malloc(void** out, size_t bytes);  // page-locked host memory
 void mem_free(void* p);                               // from either of the two; nullptr ignored
-void mem_trim();                                      // give every cached block back to the driver
+size_t mem_trim();                                    // give every cached block back to the driver; bytes released
 
 // rtw_bvh.cu: upload the flattened scene and build the LBVH on the GPU.
 int build_scene_device(rtw_scene* s, float time0, float time1, rtw_build_stats* stats);

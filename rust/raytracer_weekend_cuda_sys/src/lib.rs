@@ -147,6 +147,7 @@ extern "C" {
     pub fn rtw_scene_destroy(s: *mut rtw_scene) -> c_int;
     pub fn rtw_scene_clone(src: *const rtw_scene, device: c_int, out: *mut *mut rtw_scene) -> c_int;
     pub fn rtw_debug_live_handles() -> c_int;
+    pub fn rtw_trim_memory() -> c_int;
     // ---- textures (texture.rs, image_texture.rs)
     pub fn rtw_add_texture_solid(s: *mut rtw_scene, r: f32, g: f32, b: f32) -> c_int;
     pub fn rtw_add_texture_checker(s: *mut rtw_scene, odd: c_int, even: c_int, frequency: f32) -> c_int;

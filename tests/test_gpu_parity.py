@@ -253,6 +253,20 @@ def test_tree_rotations_lower_the_sah_cost_and_change_no_hit(gpu, oracle, monkey
         assert np.array_equal(res["4"][2], res["0"][2]) and res["4"][3] == res["0"][3]
 
 
+def test_block_cache_recycles_and_trims(gpu):
+    """rtw_mem.cu: the blocks of a destroyed scene are handed to the next one (dirty: nothing may rely on zeroed memory) and
+    rtw_trim_memory gives them back to the driver; frames are the same before and after."""
+    frames = []
+    for rep in range(3):
+        with rtw.Scene.from_name(gpu, "jumpy-balls", 16 / 9, seed=3) as s:
+            a, st = s.render(s.cameras[0], s.params(80, 45, 4, seed=2, slices=2))
+            frames.append(bits(a).copy())
+        if rep == 1:
+            assert gpu.trim_memory() >= 1   # the wavefront pool alone is > 1 MiB
+            assert gpu.trim_memory() == 0   # nothing left to release
+    assert np.array_equal(frames[0], frames[1]) and np.array_equal(frames[0], frames[2])
+
+
 def test_resolve_rgb8_matches_reference_tonemap(gpu, oracle):
     rs = np.random.RandomState(0)
     acc = (rs.uniform(0, 3, (64, 48, 3)) ** 3).astype(np.float32) * 16
