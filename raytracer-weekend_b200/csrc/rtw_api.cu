@@ -444,7 +444,7 @@ int rtw_build(rtw_scene* s, float time0, float time1, rtw_build_stats* stats) {
   }
   s->built = true;
   // the host copies of the big arrays are no longer needed
-  std::vector<float4>().swap(s->raw_geom);
+  raw_vector<float4>().swap(s->raw_geom);
   std::vector<TriShade>().swap(s->tri_shade);
   std::vector<uchar4>().swap(s->texels);
   return RTW_OK;

@@ -1,12 +1,27 @@
 // Host-side scene object behind the opaque `rtw_scene` handle of include/rtw_cuda.h:
 // the flattening state (what the emit calls recorded) and the device buffers it owns.
 #pragma once
+#include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "rtw_device.cuh"
 
 namespace rtw {
+
+// std::vector whose resize() leaves trivially constructible elements UNINITIALISED: the bulk ingest (rtw_add_triangles) grows
+// the geometry arrays by hundreds of MB and fills every element right after — from all host threads, which then also take the
+// first-touch page faults; a value-initialising resize() zeroes (and faults in) all of it on one thread first.
+template <class T>
+struct default_init_allocator : std::allocator<T> {
+  template <class U> struct rebind { using other = default_init_allocator<U>; };
+  using std::allocator<T>::allocator;
+  template <class U> void construct(U* p) noexcept(std::is_nothrow_default_constructible<U>::value) { ::new (static_cast<void*>(p)) U; }
+  template <class U, class... Args> void construct(U* p, Args&&... args) { ::new (static_cast<void*>(p)) U(std::forward<Args>(args)...); }
+};
+template <class T>
+using raw_vector = std::vector<T, default_init_allocator<T>>;
 
 struct DevBuf {
   void* p = nullptr;
@@ -48,7 +63,7 @@ struct rtw_scene {
   std::vector<uint2> inst_range;     // inst -> (first op, count) ; inst 0 = identity
   std::vector<rtw::InstOp> inst_ops;
   // primitives in canonical order
-  std::vector<float4> raw_geom;      // 3 per primitive (raw parameters, see rtw_bvh.cu)
+  rtw::raw_vector<float4> raw_geom;  // 3 per primitive (raw parameters, see rtw_bvh.cu)
   std::vector<uint32_t> prim_meta;   // type | inst << 3
   std::vector<uint32_t> prim_mat;
   std::vector<int32_t> prim_shade;   // TriShade index or -1
