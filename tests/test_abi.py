@@ -344,3 +344,20 @@ def test_rust_sys_crate_matches_the_header():
     ver = int(re.search(r"#define RTW_ABI_VERSION (\d+)", open(HDR).read()).group(1))
     assert f"pub const RTW_ABI_VERSION: c_int = {ver};" in rust_txt
     assert rtw.cuda_backend().fn("abi_version")() == ver
+
+
+def test_every_build_recipe_compiles_the_same_translation_units():
+    """csrc/Makefile (what build() runs), tools/ab_build.sh (A/B variants) and the -sys crate's build.rs (what a Rust
+    maintainer runs) must list the same .cu files — a unit missing from one of them links without rtw_mem.cu / rtw_multi.cu."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    mk = open(os.path.join(root, "raytracer-weekend_b200", "csrc", "Makefile")).read()
+    srcs = set(re.search(r"^SRCS := (.*)$", mk, re.M).group(1).split())
+    on_disk = {f for f in os.listdir(os.path.join(root, "raytracer-weekend_b200", "csrc")) if f.endswith(".cu")}
+    assert srcs == on_disk
+    ab = open(os.path.join(root, "tools", "ab_build.sh")).read()
+    assert {u + ".cu" for u in re.search(r"for f in ([\w ]+); do", ab).group(1).split()} == srcs
+    rs = open(os.path.join(root, "rust", "raytracer_weekend_cuda_sys", "build.rs")).read()
+    assert {u + ".cu" for u in re.findall(r'"(rtw_\w+)"', re.search(r"let units = \[(.*?)\];", rs, re.S).group(1))} == srcs
+    hdrs = set(re.search(r"^HDRS := (.*)$", mk, re.M).group(1).split())
+    cuh = {f for f in os.listdir(os.path.join(root, "raytracer-weekend_b200", "csrc")) if f.endswith(".cuh")}
+    assert cuh <= hdrs, "a header the kernels include is missing from the Makefile's dependency list"
