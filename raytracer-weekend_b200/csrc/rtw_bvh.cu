@@ -917,7 +917,7 @@ int build_scene_device(rtw_scene* s, float time0, float time1, rtw_build_stats* 
       }
     }
   }
-  (void)rotations;
+  if (getenv("RTW_BUILD_VERBOSE")) fprintf(stderr, "[rtw_build] %u primitives, %d rotation passes, %u rotations applied\n", n, rotate_passes, rotations);
   d.nodes4 = nullptr;
   if (const char* e = getenv("RTW_WIDE")) {  // the 4-wide records exist only for the experiment that reads them
     if (atoi(e) != 0) {

@@ -71,8 +71,8 @@ __device__ __forceinline__ uint32_t ray_sort_key(const RaySortGrid& g, v3 o, v3 
   const float qy = fminf(fmaxf((py - g.lo[1]) * g.scale[1], 0.0f), 1023.0f);
   const float qz = fminf(fmaxf((pz - g.lo[2]) * g.scale[2], 0.0f), 1023.0f);
   const uint32_t m = (expand10((uint32_t)qx) << 2) | (expand10((uint32_t)qy) << 1) | expand10((uint32_t)qz);
-  const uint32_t oct = (d.x < 0.0f ? 4u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 1u : 0u);
 #if RTW_RAYSORT_OCTANT
+  const uint32_t oct = (d.x < 0.0f ? 4u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 1u : 0u);
   return ((m >> (30 - RTW_RAYSORT_POS_BITS)) << 3) | oct;
 #else
   return m >> (30 - RTW_RAYSORT_POS_BITS);
