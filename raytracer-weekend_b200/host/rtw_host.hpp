@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdint>
 #include <map>
+#include <unordered_map>
 #include <functional>
 #include <memory>
 #include <stdexcept>
@@ -75,7 +76,7 @@ class Flattener {
   rtw_sink* sink() { return sink_; }
   void* scene() { return sink_->scene; }
   int check(int rc, const char* what);  // throws Error with the sink's message on rc < 0
-  std::map<const void*, int> texture_ids, material_ids;
+  std::unordered_map<const void*, int> texture_ids, material_ids;  // object -> emitted id (every object is emitted once)
 
  private:
   rtw_sink* sink_;
