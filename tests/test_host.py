@@ -484,3 +484,42 @@ def test_jpeg_decoder_errors(tmp_path):
         rtw.open_image(str(p))
     with pytest.raises(rtw.RtwError, match="not found"):
         rtw.open_image(str(tmp_path / "missing.jpg"))
+
+
+def test_scene_constants_match_scenes_rs():
+    """host/scenes.cpp is a transcription of console_app/src/scenes.rs, and BOTH the oracle and the CUDA path are fed by it: a
+    slip in a scene constant would be invisible to every parity test.  tests/golden/scenes_rs_literals.json holds the
+    floating-point literals of every scene function of the reference (tools/make_scene_literals.py); the mirror must use
+    exactly the same multiset of literals per scene (helpers expanded; the BASELINE variants of the cow / monument scenes may
+    add literals, never drop one)."""
+    import collections
+    import json
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = json.load(open(os.path.join(root, "tests", "golden", "scenes_rs_literals.json")))["functions"]
+    src = re.sub(r"//[^\n]*", "", open(os.path.join(root, "raytracer-weekend_b200", "host", "scenes.cpp")).read())
+    lit = re.compile(r"(?<![\w.])-?\d+\.\d+(?=f?\b)")
+    helpers = {"ground_checker()": [0.2, 0.3, 0.1, 0.9, 0.9, 0.9, 10.0],   # scenes.rs writes the checker out in every scene
+               "make_cam(": [0.0, 1.0]}                                     # ... and time0 / time1 of Camera::new
+    bodies = {}
+    for m in re.finditer(r"^World (\w+)\(", src, re.M):
+        end = src.find("\n}\n", m.start())
+        bodies[m.group(1)] = src[m.start():end]
+    names = {"wavefront_cow_obj": "wavefront_cow", "wavefront_suspension_obj": None}
+    checked = 0
+    for fn, ref_lits in ref.items():
+        mine = names.get(fn, fn)
+        if mine is None:
+            continue   # loaded through the generic OBJ path: no function of its own in the mirror
+        assert mine in bodies, f"scene {fn} has no mirror"
+        body = bodies[mine]
+        got = [float(x) for x in lit.findall(body)]
+        for call, extra in helpers.items():
+            got += extra * body.count(call)
+        want, have = collections.Counter(ref_lits), collections.Counter(got)
+        if mine in ("wavefront_cow", "textured_monument"):   # + the BASELINE.json variant (Lambertian + metal / earth sphere)
+            assert not (want - have), (fn, "missing", dict(want - have))
+        else:
+            assert want == have, (fn, "missing", dict(want - have), "extra", dict(have - want))
+        checked += 1
+    assert checked >= 11
