@@ -474,3 +474,35 @@ def test_oracle_matches_committed_render_golden(oracle):
             accum, st = s.render(s.cameras[0], s.params(w, h, spp, seed=4242, slices=slices))
         assert st.segments == segments, scene
         assert np.array_equal(bits(accum), bits(g[f"{scene}/accum"])), scene
+
+
+def test_oracle_and_kernels_carry_every_constant_of_the_reference_library():
+    """tests/golden/scenes_rs_literals.json (tools/make_scene_literals.py) also lists, per source file of raytracer_weekend_lib, the
+    floating-point literals other than 0 / 0.5 / 1 / 2: t_min 0.001 (lib.rs), the 0.0001 / 0.0002 box paddings (rectangular.rs,
+    triangular.rs), the 0.0001 re-entry offset (volumes.rs), near_zero's 1e-8 (vec3.rs), the Hermite 3.0 (perlin.rs), the checker's
+    10.0 (texture.rs), 255.0 (image_texture.rs).  An op-for-op restatement must carry each of them — in the oracle AND in the CUDA
+    sources (a constant mistyped in both would pass every parity test)."""
+    import json
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = json.load(open(os.path.join(root, "tests", "golden", "scenes_rs_literals.json")))["library_literals"]
+    want = {v for vals in lib.values() for v in vals}
+    assert {0.001, 0.0001, 0.0002, 1e-8, 3.0, 255.0} <= want
+    lit = re.compile(r"(?<![\w.])\d+\.\d*(?:e-?\d+)?f?|(?<![\w.])\d+e-?\d+f?")
+
+    def literals(paths):
+        got = set()
+        for p in paths:
+            text = re.sub(r"//[^\n]*", "", open(os.path.join(root, p)).read())
+            got |= {float(x.rstrip("f")) for x in lit.findall(text)}
+        return got
+
+    oracle = literals(["oracle/rtw_oracle.hpp", "oracle/oracle_capi.cpp", "raytracer-weekend_b200/host/rtw_host.cpp",
+                       "raytracer-weekend_b200/host/scenes.cpp", "raytracer-weekend_b200/host/rtw_host.hpp"])
+    cuda = literals(["raytracer-weekend_b200/csrc/rtw_device.cuh", "raytracer-weekend_b200/csrc/rtw_bvh.cu",
+                     "raytracer-weekend_b200/csrc/rtw_render.cu", "raytracer-weekend_b200/csrc/rtw_traverse.cuh",
+                     "raytracer-weekend_b200/csrc/rtw_api.cu", "raytracer-weekend_b200/host/rtw_host.cpp",
+                     "raytracer-weekend_b200/host/scenes.cpp", "raytracer-weekend_b200/host/rtw_host.hpp"])
+    assert not (want - oracle), ("oracle lacks", want - oracle)
+    assert not (want - cuda), ("CUDA path lacks", want - cuda)
