@@ -32,3 +32,15 @@ def test_non_zero_ranks_of_the_reference_arm_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_the_gpu_arm_fails_loudly_without_a_device():
+    """No CPU fallback anywhere on the product path: without a CUDA device the b200 arm must stop with an error, not print a line."""
+    from conftest import HAS_GPU
+    if HAS_GPU:
+        import pytest
+        pytest.skip("needs a machine WITHOUT a GPU")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0", "--no-cpu-baseline",
+                        "--no-per-config"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode != 0
+    assert not [l for l in r.stdout.splitlines() if l.startswith("{")]
