@@ -1,0 +1,343 @@
+"""A SECOND restatement of the reference's primitive hit() functions, in numpy float32, written from the Rust text alone and compared
+BIT FOR BIT with the C++ oracle on random rays.  numpy evaluates every float32 operation separately (no contraction), so agreement
+means the two transcriptions order the operations the same way — a slip in one of them (a swapped operand, a different association,
+a reciprocal instead of a division) shows up as differing bits.  Not a substitute for running the reference (no Rust toolchain here:
+DESIGN.md §2), but independent of the oracle's own golden files."""
+import numpy as np
+import pytest
+
+import raytracer_weekend_b200 as rtw
+
+F = np.float32
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def _dot(a, b):      # vec3.rs:46-48   e0*e0 + e1*e1 + e2*e2, left to right
+    return (a[..., 0] * b[..., 0] + a[..., 1] * b[..., 1]) + a[..., 2] * b[..., 2]
+
+
+def _cross(a, b):    # vec3.rs:50-56
+    return np.stack([a[..., 1] * b[..., 2] - a[..., 2] * b[..., 1],
+                     a[..., 2] * b[..., 0] - a[..., 0] * b[..., 2],
+                     a[..., 0] * b[..., 1] - a[..., 1] * b[..., 0]], axis=-1)
+
+
+def _at(o, d, t):    # ray.rs:25-27   origin + t * direction
+    return o + t[:, None] * d
+
+
+def _face(d, outward):   # hittable/mod.rs:32-47
+    front = _dot(d, outward) < 0
+    return front, np.where(front[:, None], outward, -outward)
+
+
+def _rays(n, seed, lo=-3.0, hi=3.0):
+    rs = np.random.RandomState(seed)
+    o = rs.uniform(lo, hi, (n, 3)).astype(F)
+    target = rs.uniform(-1.0, 1.0, (n, 3)).astype(F)
+    d = (target - o).astype(F)
+    return o, d
+
+
+def _trace(scene, o, d, t_min=0.001, t_max=np.inf, time=0.0):
+    return scene.trace_closest(rtw.make_rays(o, d, time, t_min, t_max))
+
+
+def test_sphere_hit_bitwise(oracle):
+    """spherical.rs:18-60 (hit_sphere), centre / radius arbitrary, rays from outside and inside"""
+    c = np.array([0.3, -0.2, 0.1], F)
+    r = F(1.25)
+    with oracle.new_scene() as s:
+        s.sphere(tuple(float(x) for x in c), float(r), s.lambertian_rgb(.5, .5, .5))
+        s.build()
+        o, d = _rays(20000, 1)
+        h = _trace(s, o, d)
+    t_min, t_max = F(0.001), F(np.inf)
+    oc = o - c
+    a = _dot(d, d)
+    half_b = _dot(oc, d)
+    cc = _dot(oc, oc) - r * r
+    with np.errstate(invalid="ignore"):
+        disc = half_b * half_b - a * cc
+        sq = np.sqrt(np.maximum(disc, F(0)))
+        root = (-half_b - sq) / a
+        far = (-half_b + sq) / a
+    use_far = (root < t_min) | (t_max < root)
+    root = np.where(use_far, far, root)
+    hit = (disc >= 0) & ~((root < t_min) | (t_max < root))
+    assert np.array_equal(h["prim_id"] >= 0, hit) and hit.sum() > 5000 and use_far[hit].sum() > 100
+    p = _at(o, d, root)
+    outward = (p - c) / r
+    front, normal = _face(d, outward)
+    assert np.array_equal(_bits(h["t"][hit]), _bits(root[hit]))
+    assert np.array_equal(_bits(h["p"][hit]), _bits(p[hit]))
+    assert np.array_equal(_bits(h["normal"][hit]), _bits(normal[hit]))
+    assert np.array_equal(h["front_face"][hit] != 0, front[hit])
+    # get_sphere_uv (spherical.rs:62-78): libm on both sides, so a tolerance instead of bits
+    with np.errstate(invalid="ignore"):   # rows that are no hit carry NaN
+        theta = np.arccos(-outward[:, 1].astype(np.float64))
+        phi = np.arctan2(-outward[:, 2].astype(np.float64), outward[:, 0].astype(np.float64)) + np.pi
+    np.testing.assert_allclose(h["u"][hit], (phi / (2 * np.pi))[hit], atol=2e-6)
+    np.testing.assert_allclose(h["v"][hit], (theta / np.pi)[hit], atol=2e-6)
+
+
+def test_triangle_hit_bitwise(oracle):
+    """triangular.rs:97-138 with the default normals / uvs of triangular.rs:42-65"""
+    va, vb, vc = (np.array(v, F) for v in ([-1.0, -0.5, 0.2], [1.5, -0.25, -0.3], [0.1, 1.75, 0.4]))
+    with oracle.new_scene() as s:
+        s.triangles([list(map(float, np.concatenate([va, vb, vc])))], s.lambertian_rgb(.5, .5, .5))
+        s.build()
+        o, d = _rays(20000, 2)
+        h = _trace(s, o, d)
+    t_min, t_max = F(0.001), F(np.inf)
+    ab, ac = vb - va, vc - va
+    n = _cross(ab, ac)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        det = -_dot(d, n[None, :])
+        inv = F(1.0) / det
+        ao = o - va
+        aod = _cross(ao, d)
+        u = _dot(ac[None, :], aod) * inv
+        v = (-_dot(ab[None, :], aod)) * inv
+        t = _dot(ao, n[None, :]) * inv
+    hit = ~((t < t_min) | (t > t_max)) & (t >= 0) & (u >= 0) & (v >= 0) & ((u + v) <= 1)
+    assert np.array_equal(h["prim_id"] >= 0, hit) and hit.sum() > 2000
+    p = _at(o, d, t)
+    # interpolate_barycentric over three copies of the face normal (triangular.rs:125-131, 47-55): (1-u-v) n + u n + v n
+    w0 = F(1.0) - u - v
+    hit_normal = (w0[:, None] * n[None, :] + u[:, None] * n[None, :]) + v[:, None] * n[None, :]
+    front, normal = _face(d, hit_normal)
+    assert np.array_equal(_bits(h["t"][hit]), _bits(t[hit]))
+    assert np.array_equal(_bits(h["p"][hit]), _bits(p[hit]))
+    assert np.array_equal(h["front_face"][hit] != 0, front[hit])
+    assert np.array_equal(_bits(h["normal"][hit]), _bits(normal[hit]))
+    # default uvs (0,0), (1,0), (0,1) through the same interpolation (triangular.rs:57-65, 132)
+    zero = np.zeros_like(u)
+    tu = (w0 * zero + u * F(1.0)) + v * zero
+    tv = (w0 * zero + u * zero) + v * F(1.0)
+    assert np.array_equal(_bits(h["u"][hit]), _bits(tu[hit])) and np.array_equal(_bits(h["v"][hit]), _bits(tv[hit]))
+
+
+@pytest.mark.parametrize("kind", ["xy", "xz", "yz"])
+def test_rectangle_hit_bitwise(oracle, kind):
+    """rectangular.rs:27-57 / 78-108 / 129-159"""
+    a0, a1, b0, b1, k = (F(x) for x in (-0.75, 1.25, -1.5, 0.5, 0.3))
+    with oracle.new_scene() as s:
+        m = s.lambertian_rgb(.5, .5, .5)
+        getattr(s, f"{kind}_rect")(float(a0), float(a1), float(b0), float(b1), float(k), m)
+        s.build()
+        o, d = _rays(20000, 3)
+        h = _trace(s, o, d)
+    ia, ib, ik = {"xy": (0, 1, 2), "xz": (0, 2, 1), "yz": (1, 2, 0)}[kind]
+    t_min, t_max = F(0.001), F(np.inf)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t = (k - o[:, ik]) / d[:, ik]
+        a = o[:, ia] + t * d[:, ia]
+        b = o[:, ib] + t * d[:, ib]
+    hit = ~((t < t_min) | (t > t_max)) & ~((a < a0) | (a > a1) | (b < b0) | (b > b1))
+    assert np.array_equal(h["prim_id"] >= 0, hit) and hit.sum() > 1000
+    p = _at(o, d, t)
+    outward = np.zeros((len(o), 3), F)
+    outward[:, ik] = 1.0
+    front, normal = _face(d, outward)
+    assert np.array_equal(_bits(h["t"][hit]), _bits(t[hit]))
+    assert np.array_equal(_bits(h["p"][hit]), _bits(p[hit]))
+    assert np.array_equal(_bits(h["normal"][hit]), _bits(normal[hit]))
+    assert np.array_equal(h["front_face"][hit] != 0, front[hit])
+    assert np.array_equal(_bits(h["u"][hit]), _bits(((a - a0) / (a1 - a0))[hit]))
+    assert np.array_equal(_bits(h["v"][hit]), _bits(((b - b0) / (b1 - b0))[hit]))
+
+
+def test_aabb_hit_matches(oracle):
+    """aabb.rs:23-48: reciprocal per axis, swap on a negative reciprocal, f32::max / min (which drop NaN), reject on t_max <= t_min"""
+    import ctypes as C
+    rs = np.random.RandomState(4)
+    n = 4000
+    lo = rs.uniform(-1.0, 0.5, (n, 3)).astype(F)
+    hi = (lo + rs.uniform(0.0, 1.5, (n, 3)).astype(F)).astype(F)
+    o, d = _rays(n, 5)
+    d[rs.rand(n) < 0.1, 0] = 0.0                      # rays parallel to an axis: 1/0 = inf, 0 * inf = NaN paths
+    on_face = rs.rand(n) < 0.05
+    o[on_face, 0] = lo[on_face, 0]
+    rays = rtw.make_rays(o, d, 0.0, 0.001, np.inf)
+    got = np.array([oracle.fn("aabb_hit")((C.c_float * 3)(*map(float, lo[i])), (C.c_float * 3)(*map(float, hi[i])),
+                                          rays[i:i + 1].ctypes.data) for i in range(n)], bool)
+    t_min = np.full(n, 0.001, F)
+    t_max = np.full(n, np.inf, F)
+    alive = np.ones(n, bool)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for a in range(3):
+            inv = F(1.0) / d[:, a]
+            t0 = (lo[:, a] - o[:, a]) * inv
+            t1 = (hi[:, a] - o[:, a]) * inv
+            swap = inv < 0
+            t0, t1 = np.where(swap, t1, t0), np.where(swap, t0, t1)
+            t_min = np.where(np.isnan(t0), t_min, np.where(np.isnan(t_min), t0, np.maximum(t0, t_min)))   # f32::max
+            t_max = np.where(np.isnan(t1), t_max, np.where(np.isnan(t_max), t1, np.minimum(t1, t_max)))   # f32::min
+            alive &= ~(t_max <= t_min)
+    assert np.array_equal(got, alive) and 500 < alive.sum() < n - 500
+
+
+@pytest.mark.parametrize("args", [
+    ((13, 2, 3), (0, 0, 0), (0, 1, 0), 20.0, 16 / 9, 0.1, 10.0),
+    ((278, 278, -800), (278, 278, 0), (0, 1, 0), 40.0, 1.0, 0.0, 10.0),
+    ((-5, -30, 25), (0, 0, 5), (1, 0, 0), 40.0, 3840 / 2160, 0.0, 10.0),
+    ((478, 278, -600), (278, 278, 278), (0, 1, 0), 40.0, 1.0, 1.0, 1077.6),
+])
+def test_camera_new_against_numpy(oracle, args):
+    """camera.rs:25-64.  The frame (w, u, v), origin and lens radius use only IEEE-exact operations: bit for bit.  The viewport
+    goes through tan(): 1e-6 relative."""
+    look_from, look_at, up, vfov, aspect, aperture, focus = args
+    cam = oracle.camera_new(*args)
+    lf, la, upv = (np.array(x, F) for x in (look_from, look_at, up))
+
+    def unit(a):   # vec3.rs:85-87: a / length(a)
+        return a / np.sqrt(_dot(a, a))
+
+    w = unit(lf - la)
+    u = unit(_cross(upv, w))
+    v = _cross(w, u)
+    assert np.array_equal(_bits(np.array(cam.w[:], F)), _bits(w))
+    assert np.array_equal(_bits(np.array(cam.u[:], F)), _bits(u))
+    assert np.array_equal(_bits(np.array(cam.v[:], F)), _bits(v))
+    assert np.array_equal(_bits(np.array(cam.origin[:], F)), _bits(lf))
+    assert F(cam.lens_radius) == F(aperture) / F(2.0)
+    theta = F(vfov) * (F(np.pi) / F(180.0))               # f32::to_radians
+    h = F(np.tan(np.float64(theta / F(2.0))))
+    vh = F(2.0) * h
+    vw = F(aspect) * vh
+    horizontal = (F(focus) * vw) * u
+    vertical = (F(focus) * vh) * v
+    llc = ((lf - horizontal / F(2.0)) - vertical / F(2.0)) - F(focus) * w
+    np.testing.assert_allclose(cam.horizontal[:], horizontal, rtol=2e-6, atol=1e-6)
+    np.testing.assert_allclose(cam.vertical[:], vertical, rtol=2e-6, atol=1e-6)
+    np.testing.assert_allclose(cam.lower_left_corner[:], llc, rtol=2e-6, atol=2e-4)
+
+
+# ---- Material::scatter (material.rs:40-147) from the path stream ---------------------------------------------------------------
+# The random STREAM is this repo's specification (Philox keyed by pixel / sample, stage = bounce + 1: DESIGN.md §2), so the draws
+# are taken from the oracle's own generator; what is re-derived here from the Rust text is everything done WITH them.
+W, H, SEED = 48, 27, 77
+
+
+def _draws(oracle, pixel, stage, kind, n, lo=-1.0, hi=1.0):
+    import ctypes as C
+    u = np.zeros(n, np.uint32)
+    f = np.zeros(n, F)
+    oracle.fn("rng_draws")(SEED, int(pixel), 0, int(stage), kind, lo, hi, n, u.ctypes.data, f.ctypes.data)
+    return f
+
+
+def _unit(a):
+    return a / np.sqrt(_dot(a, a))
+
+
+def _in_unit_sphere(g):   # vec3.rs:101-108 over the sequential gen_range(-1, 1) draws g
+    for k in range(len(g) // 3):
+        p = g[3 * k:3 * k + 3]
+        if _dot(p, p) < F(1.0):
+            return p, 3 * (k + 1)
+    raise AssertionError("not enough draws")
+
+
+def _reflect(v, n):       # vec3.rs:140-142   v - (2 * dot(v, n)) * n
+    return v - (F(2.0) * _dot(v, n)) * n
+
+
+def _scatter_scene(oracle, material):
+    s = oracle.new_scene()
+    m = material(s)
+    s.sphere((0.0, 0.0, 0.0), 1.5, m)
+    s.build()
+    cam = oracle.camera_new((0.5, 0.8, -6.0), (0, 0, 0), (0, 1, 0), 35.0, W / H, 0.0, 6.0)
+    r0 = oracle.capture_rays(s, cam, W, H, SEED, 0, 0)
+    r1 = oracle.capture_rays(s, cam, W, H, SEED, 0, 1)
+    hits = s.trace_closest(r0)
+    return s, r0, r1, hits
+
+
+def _pixel_of(idx):       # the reference's pixel order: rows top-down in the buffer, Pixel.row bottom-up (lib.rs:58)
+    y_top, col = divmod(idx, W)
+    return (H - 1 - y_top) * W + col
+
+
+def test_lambertian_scatter_bitwise(oracle):
+    """material.rs:40-56: normal + random_unit_vector, the near-zero guard, origin = hit point, time kept"""
+    s, r0, r1, hits = _scatter_scene(oracle, lambda s: s.lambertian_rgb(.5, .5, .5))
+    checked = 0
+    for i in np.nonzero(hits["prim_id"] >= 0)[0]:
+        g = _draws(oracle, _pixel_of(i), 1, 2, 90)
+        p, _ = _in_unit_sphere(g)
+        d = hits["normal"][i] + _unit(p)
+        if (np.abs(d) < F(1e-8)).all():
+            d = hits["normal"][i]
+        assert r1["t_max"][i] > r1["t_min"][i]
+        assert np.array_equal(_bits(r1["origin"][i]), _bits(hits["p"][i]))
+        assert np.array_equal(_bits(r1["direction"][i]), _bits(d)), i
+        assert r1["time"][i] == r0["time"][i]
+        checked += 1
+    assert checked > 200
+    assert (r1["t_max"][hits["prim_id"] < 0] < r1["t_min"][hits["prim_id"] < 0]).all()   # a miss ends the path
+    s.close()
+
+
+@pytest.mark.parametrize("fuzz", [0.0, 0.4, 1.0])
+def test_metal_scatter_bitwise(oracle, fuzz):
+    """material.rs:77-98: reflect(unit(d), n) + fuzz * random_in_unit_sphere (drawn even for fuzz 0); absorbed unless dot(out, n) > 0"""
+    s, r0, r1, hits = _scatter_scene(oracle, lambda s: s.metal(.8, .8, .9, fuzz))
+    alive = absorbed = 0
+    for i in np.nonzero(hits["prim_id"] >= 0)[0]:
+        n = hits["normal"][i]
+        g = _draws(oracle, _pixel_of(i), 1, 2, 90)
+        p, _ = _in_unit_sphere(g)
+        out = _reflect(_unit(r0["direction"][i]), n) + F(fuzz) * p
+        if _dot(out, n) > 0:
+            assert r1["t_max"][i] > r1["t_min"][i]
+            assert np.array_equal(_bits(r1["direction"][i]), _bits(out)), i
+            assert np.array_equal(_bits(r1["origin"][i]), _bits(hits["p"][i]))
+            alive += 1
+        else:
+            assert r1["t_max"][i] < r1["t_min"][i]
+            absorbed += 1
+    assert alive > 200 and (fuzz < 1.0 or absorbed > 0)
+    s.close()
+
+
+def test_dielectric_scatter_bitwise(oracle):
+    """material.rs:100-147 + vec3.rs:144-151: refraction ratio by face, Schlick with powi(5) = x * (x^2)^2, the draw only when
+    refraction is possible (short circuit), reflect / refract"""
+    ir = F(1.5)
+    s, r0, r1, hits = _scatter_scene(oracle, lambda s: s.dielectric(float(ir)))
+    reflected = refracted = 0
+    for i in np.nonzero(hits["prim_id"] >= 0)[0]:
+        n = hits["normal"][i]
+        ratio = F(1.0) / ir if hits["front_face"][i] else ir
+        ud = _unit(r0["direction"][i])
+        cos_t = np.minimum(_dot(-ud, n), F(1.0))
+        sin_t = np.sqrt(F(1.0) - cos_t * cos_t)
+        cannot = ratio * sin_t > F(1.0)
+        if not cannot:
+            r0_ = (F(1.0) - ratio) / (F(1.0) + ratio)
+            r0_ = r0_ * r0_
+            x = F(1.0) - cos_t
+            x2 = x * x
+            refl = r0_ + (F(1.0) - r0_) * (x * (x2 * x2))      # powi(5): compiler-rt's square-and-multiply
+            xi = _draws(oracle, _pixel_of(i), 1, 1, 1)[0]
+            cannot = refl > xi
+        if cannot:
+            out = _reflect(ud, n)
+            reflected += 1
+        else:
+            cos2 = np.minimum(_dot(-ud, n), F(1.0))
+            perp = ratio * (ud + cos2 * n)
+            par = (-np.sqrt(np.abs(F(1.0) - _dot(perp, perp)))) * n
+            out = perp + par
+            refracted += 1
+        assert r1["t_max"][i] > r1["t_min"][i]
+        assert np.array_equal(_bits(r1["direction"][i]), _bits(out)), (i, bool(cannot))
+        assert np.array_equal(_bits(r1["origin"][i]), _bits(hits["p"][i]))
+    assert refracted > 150 and reflected > 5
+    s.close()
