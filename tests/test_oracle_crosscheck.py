@@ -341,3 +341,158 @@ def test_dielectric_scatter_bitwise(oracle):
         assert np.array_equal(_bits(r1["origin"][i]), _bits(hits["p"][i]))
     assert refracted > 150 and reflected > 5
     s.close()
+
+
+# ---- the whole path: lib.rs:78-117 (sample_pixel, sample_ray), camera.rs:66-74 (get_ray), the list rule of hittable/mod.rs:57-69 --
+# A tiny scene path-traced by a second, scalar numpy-float32 implementation written from the Rust text; the frame must equal the
+# oracle's RECURSIVE integrator bit for bit (same operations in the same order) — and the oracle's iterative form, which is what the
+# GPU is compared with, within the bound test_recursive_vs_iterative_integrator states.
+class _Stream:
+    """The repo's random stream: raw Philox words from the oracle's generator, mapped like rand's f32 distributions."""
+
+    def __init__(self, oracle, seed, pixel, sample, stage):
+        import ctypes as C
+        self.words = np.zeros(256, np.uint32)
+        dummy = np.zeros(256, F)
+        oracle.fn("rng_draws")(seed, int(pixel), int(sample), int(stage), 0, 0.0, 1.0, 256, self.words.ctypes.data, dummy.ctypes.data)
+        self.i = 0
+
+    def _next(self):
+        w = self.words[self.i]
+        self.i += 1
+        return w
+
+    def gen(self):                                   # rand Standard: 24 bits
+        return F(int(self._next()) >> 8) * F(1.0 / 16777216.0)
+
+    def gen_range(self, lo, hi):                     # rand UniformFloat::sample_single
+        v12 = np.array([0x3F800000 | (int(self._next()) >> 9)], np.uint32).view(F)[0]
+        scale = F(hi) - F(lo)
+        return v12 * scale + (F(lo) - scale)
+
+
+def _v(*x):
+    return np.array(x, F)
+
+
+def _sphere_hit(o, d, c, r, t_min, t_max):
+    oc = o - c
+    a = _dot(d, d)
+    half_b = _dot(oc, d)
+    cc = _dot(oc, oc) - r * r
+    disc = half_b * half_b - a * cc
+    if disc < 0:
+        return None
+    sq = np.sqrt(disc)
+    root = (-half_b - sq) / a
+    if root < t_min or t_max < root:
+        root = (-half_b + sq) / a
+        if root < t_min or t_max < root:
+            return None
+    p = o + root * d
+    outward = (p - c) / r
+    front = _dot(d, outward) < 0
+    return root, p, (outward if front else -outward), front
+
+
+def _xz_rect_hit(o, d, x0, x1, z0, z1, k, t_min, t_max):
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t = (k - o[1]) / d[1]
+    if t < t_min or t > t_max:
+        return None
+    x = o[0] + t * d[0]
+    z = o[2] + t * d[2]
+    if x < x0 or x > x1 or z < z0 or z > z1:
+        return None
+    outward = _v(0, 1, 0)
+    front = _dot(d, outward) < 0
+    return t, o + t * d, (outward if front else -outward), front
+
+
+def test_tiny_path_tracer_equals_the_oracle_frame(oracle):
+    w, h, spp, seed = 12, 8, 3, 4242
+    background = _v(0.3, 0.4, 0.6)
+    ground = dict(kind="sphere", c=_v(0, -100.5, -1), r=F(100.0), mat=("lambert", _v(0.8, 0.7, 0.2)))
+    ball = dict(kind="sphere", c=_v(0.3, 0.0, -1.2), r=F(0.5), mat=("metal", _v(0.8, 0.8, 0.9), F(0.3)))
+    lamp = dict(kind="xz", x0=F(-1.5), x1=F(1.5), z0=F(-2.5), z1=F(0.5), k=F(1.6), mat=("light", _v(3.0, 2.5, 2.0)))
+    objects = [ground, ball, lamp]
+    with oracle.new_scene() as s:
+        s.sphere(tuple(map(float, ground["c"])), float(ground["r"]), s.lambertian_rgb(0.8, 0.7, 0.2))
+        s.sphere(tuple(map(float, ball["c"])), float(ball["r"]), s.metal(0.8, 0.8, 0.9, 0.3))
+        s.xz_rect(-1.5, 1.5, -2.5, 0.5, 1.6, s.diffuse_light(s.texture_solid(3.0, 2.5, 2.0)))
+        s.build()
+        cam = oracle.camera_new((0.2, 0.6, 2.5), (0, 0, -1), (0, 1, 0), 50.0, w / h, 0.15, 3.4)
+        p = s.params(w, h, spp, seed=seed, slices=1, background=tuple(map(float, background)))
+        frame_rec, _ = oracle.render_ex(s, cam, p, mode=0, integrator=1)
+        frame_it, _ = oracle.render_ex(s, cam, p, mode=0, integrator=0)
+    origin, llc, hor, ver = (np.array(x[:], F) for x in (cam.origin, cam.lower_left_corner, cam.horizontal, cam.vertical))
+    cu, cv, lens = np.array(cam.u[:], F), np.array(cam.v[:], F), F(cam.lens_radius)
+
+    def world_hit(o, d, t_min, t_max):               # hittable/mod.rs:57-69
+        best, closest = None, t_max
+        for ob in objects:
+            if ob["kind"] == "sphere":
+                r = _sphere_hit(o, d, ob["c"], ob["r"], t_min, closest)
+            else:
+                r = _xz_rect_hit(o, d, ob["x0"], ob["x1"], ob["z0"], ob["z1"], ob["k"], t_min, closest)
+            if r is not None:
+                closest = r[0]
+                best = (r, ob)
+        return best
+
+    def sample_ray(o, d, pixel, sample, depth):      # lib.rs:97-117, recursive as written
+        if depth == 0:
+            return _v(0, 0, 0)
+        hit = world_hit(o, d, F(0.001), F(np.inf))
+        if hit is None:
+            return background
+        (t, pnt, normal, front), ob = hit
+        rng = _Stream(oracle, seed, pixel, sample, 50 - depth + 1)
+        mat = ob["mat"]
+        if mat[0] == "light":                        # light_source.rs: emits, never scatters
+            return mat[1]
+        if mat[0] == "lambert":
+            while True:
+                q = _v(rng.gen_range(-1, 1), rng.gen_range(-1, 1), rng.gen_range(-1, 1))
+                if _dot(q, q) < 1:
+                    break
+            out = normal + _unit(q)
+            if (np.abs(out) < F(1e-8)).all():
+                out = normal
+            att = mat[1]
+        else:
+            refl = _reflect(_unit(d), normal)
+            while True:
+                q = _v(rng.gen_range(-1, 1), rng.gen_range(-1, 1), rng.gen_range(-1, 1))
+                if _dot(q, q) < 1:
+                    break
+            out = refl + mat[2] * q
+            if not _dot(out, normal) > 0:
+                return _v(0, 0, 0)                   # emitted = black
+            att = mat[1]
+        return _v(0, 0, 0) + att * sample_ray(pnt, out, pixel, sample, depth - 1)
+
+    frame = np.zeros((h, w, 3), F)
+    for y_top in range(h):
+        row = h - 1 - y_top
+        for col in range(w):
+            pixel = row * w + col
+            color = _v(0, 0, 0)
+            for smp in range(spp):                   # lib.rs:83-88
+                rng = _Stream(oracle, seed, pixel, smp, 0)
+                u = (F(col) + rng.gen()) / F(w - 1)
+                v = (F(row) + rng.gen()) / F(h - 1)
+                while True:                          # camera.rs:66-74, vec3.rs:124-131
+                    rd = _v(rng.gen_range(-1, 1), rng.gen_range(-1, 1), 0)
+                    if _dot(rd, rd) < 1:
+                        break
+                rd = lens * rd
+                offset = cu * rd[0] + cv * rd[1]
+                time = rng.gen_range(float(cam.time0), float(cam.time1))
+                o = origin + offset
+                d = (((llc + u * hor) + v * ver) - origin) - offset
+                color = color + sample_ray(o, d, pixel, smp, 50)
+            frame[y_top, col] = color
+    assert np.array_equal(_bits(frame), _bits(frame_rec)), "the recursive integrator differs from the Rust text"
+    np.testing.assert_allclose(frame_it, frame_rec, rtol=1e-4, atol=1e-5)     # iterative form: same terms, another association
+    assert len(np.unique(_bits(frame).reshape(-1, 3), axis=0)) > 12            # a real picture (sky, lamp, ground, metal, multi-bounce mixes)
