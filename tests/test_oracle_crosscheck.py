@@ -496,3 +496,86 @@ def test_tiny_path_tracer_equals_the_oracle_frame(oracle):
     assert np.array_equal(_bits(frame), _bits(frame_rec)), "the recursive integrator differs from the Rust text"
     np.testing.assert_allclose(frame_it, frame_rec, rtol=1e-4, atol=1e-5)     # iterative form: same terms, another association
     assert len(np.unique(_bits(frame).reshape(-1, 3), axis=0)) > 12            # a real picture (sky, lamp, ground, metal, multi-bounce mixes)
+
+
+def test_translation_and_rotation_wrappers_bitwise(oracle):
+    """transformations.rs:22-37, 113-147: Translation(YRotation(sphere)) as in scenes.rs' Cornell boxes — the ray is moved and rotated
+    into the object's space, the hit point and normal come back out, and BOTH wrappers re-run new_with_face_normal on the normal the
+    inner hit already flipped (so a hit through a wrapper always reports front_face = true: the reference's quirk, kept)."""
+    c, r = _v(0.2, -0.1, 0.3), F(0.9)
+    off = _v(0.7, -0.4, 1.1)
+    sin_t, cos_t = F(np.sin(np.float64(0.4))), F(np.cos(np.float64(0.4)))
+    with oracle.new_scene() as s:
+        s.push_translation(tuple(map(float, off)))
+        s.push_rotation_y_sincos(float(sin_t), float(cos_t))
+        s.sphere(tuple(map(float, c)), float(r), s.lambertian_rgb(.5, .5, .5))
+        s.pop_transform()
+        s.pop_transform()
+        s.build()
+        o, d = _rays(6000, 9)
+        h = _trace(s, o, d)
+    n_hit = 0
+    for i in range(len(o)):
+        o1 = o[i] - off                                              # Translation::hit
+        o2 = _v(cos_t * o1[0] - sin_t * o1[2], o1[1], sin_t * o1[0] + cos_t * o1[2])   # YRotation::hit
+        d2 = _v(cos_t * d[i][0] - sin_t * d[i][2], d[i][1], sin_t * d[i][0] + cos_t * d[i][2])
+        got = _sphere_hit(o2, d2, c, r, F(0.001), F(np.inf))
+        if got is None:
+            assert h["prim_id"][i] < 0
+            continue
+        t, p, normal, _front = got
+        p_r = _v(cos_t * p[0] + sin_t * p[2], p[1], -sin_t * p[0] + cos_t * p[2])
+        n_r = _v(cos_t * normal[0] + sin_t * normal[2], normal[1], -sin_t * normal[0] + cos_t * normal[2])
+        front_r = _dot(d2, n_r) < 0                                  # against the ROTATED ray (transformations.rs:137-146)
+        n_r = n_r if front_r else -n_r
+        p_t = p_r + off
+        front_t = _dot(d[i], n_r) < 0                                # Translation: against the translated ray (same direction)
+        n_t = n_r if front_t else -n_r
+        assert h["prim_id"][i] == 0 and _bits(h["t"][i:i + 1])[0] == _bits(np.array([t], F))[0]
+        assert np.array_equal(_bits(h["p"][i]), _bits(p_t)), i
+        assert np.array_equal(_bits(h["normal"][i]), _bits(n_t)), i
+        assert bool(h["front_face"][i]) == bool(front_t)
+        n_hit += 1
+    assert n_hit > 500
+
+
+def test_moving_sphere_bitwise(oracle):
+    """spherical.rs:117-123 + hit_sphere: centre(time) = c0 + ((time - t0) / (t1 - t0)) * (c1 - c0)"""
+    c0, c1, t0, t1, r = _v(-0.3, 0.0, 0.2), _v(0.4, 0.6, 0.1), F(0.25), F(1.5), F(0.8)
+    with oracle.new_scene() as s:
+        s.moving_sphere(tuple(map(float, c0)), float(t0), tuple(map(float, c1)), float(t1), float(r), s.lambertian_rgb(.5, .5, .5))
+        s.build()
+        o, d = _rays(4000, 11)
+        times = np.random.RandomState(12).uniform(0.0, 2.0, len(o)).astype(F)
+        rays = rtw.make_rays(o, d, 0.0, 0.001, np.inf)
+        rays["time"] = times
+        h = s.trace_closest(rays)
+    n_hit = 0
+    for i in range(len(o)):
+        centre = c0 + ((times[i] - t0) / (t1 - t0)) * (c1 - c0)
+        got = _sphere_hit(o[i], d[i], centre, r, F(0.001), F(np.inf))
+        assert (got is None) == (h["prim_id"][i] < 0)
+        if got is not None:
+            assert _bits(h["t"][i:i + 1])[0] == _bits(np.array([got[0]], F))[0]
+            assert np.array_equal(_bits(h["p"][i]), _bits(got[1])) and np.array_equal(_bits(h["normal"][i]), _bits(got[2]))
+            n_hit += 1
+    assert n_hit > 400
+
+
+def test_tonemap_against_numpy(oracle):
+    """console_app/src/main.rs:73-86: sqrt(sum / spp) clamped to [0, 0.999], * 255.999 as u8"""
+    import ctypes as C
+    rs = np.random.RandomState(3)
+    acc = np.concatenate([rs.uniform(0, 40, 3000), [0.0, -1.0, 1e9, np.nan, 16.0, 15.99999]]).astype(F)
+    n = len(acc) // 3 * 3
+    acc = acc[:n]
+    spp = 16
+    out = np.zeros(n, np.uint8)
+    oracle.fn("resolve_rgb8").argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+    oracle.fn("resolve_rgb8")(None, acc.ctypes.data, n // 3, 1, spp, out.ctypes.data)
+    with np.errstate(invalid="ignore"):
+        c = np.sqrt((F(1.0) / F(spp)) * acc)
+        cl = np.where(c < 0, F(0), np.where(c > F(0.999), F(0.999), c))
+        v = F(255.999) * cl
+    want = np.where(np.isnan(v), 0, np.clip(np.nan_to_num(v), 0, 255)).astype(np.uint8)
+    assert np.array_equal(out, want)
