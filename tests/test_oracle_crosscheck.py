@@ -579,3 +579,80 @@ def test_tonemap_against_numpy(oracle):
         v = F(255.999) * cl
     want = np.where(np.isnan(v), 0, np.clip(np.nan_to_num(v), 0, 255)).astype(np.uint8)
     assert np.array_equal(out, want)
+
+
+# ---- textures: perlin.rs, texture.rs, image_texture.rs ----------------------------------------------------------------------------
+def _perlin_noise(grad, perm, p):          # perlin.rs:50-75, 91-123
+    fl = np.floor(p)
+    base = fl.astype(np.int64)             # to_i64().to_usize(): the wrap of a negative index is undone by & 255
+    pw = p - fl
+    pf = (pw * pw) * (_v(3, 3, 3) - F(2.0) * pw)       # filter_hermit
+    accum = F(0.0)
+    one = _v(1, 1, 1)
+    for a in range(2):
+        for r in range(2):
+            for c in range(2):
+                idx = (base + np.array([a, r, c])) & 255
+                g = grad[perm[0][idx[0]] ^ perm[1][idx[1]] ^ perm[2][idx[2]]]
+                cur = _v(a, r, c)
+                weight_v = pf - cur        # (the shadowed, FILTERED point: perlin.rs:92,103)
+                blend = cur * pf + (one - cur) * (one - pf)
+                accum = accum + ((blend[0] * blend[1]) * blend[2]) * _dot(g, weight_v)
+    return accum
+
+
+def _turbulence(grad, perm, p, depth=7):   # perlin.rs:77-89
+    accum, temp, weight = F(0.0), p.copy(), F(1.0)
+    for _ in range(depth):
+        accum = accum + weight * _perlin_noise(grad, perm, temp)
+        weight = weight * F(0.5)
+        temp = temp * F(2.0)
+    return np.abs(accum)
+
+
+def test_noise_texture_against_numpy(oracle):
+    """texture.rs:83-95 over perlin.rs: 0.5 * (1 + sin(scale * z + 10 * turbulence(p, 7))).  Everything inside the sine is IEEE-exact
+    arithmetic; the sine itself is libm on both sides (correctly rounded almost always): >= 98 % of the samples must agree bit for
+    bit and the rest within 2 ulp — an operation out of order inside noise() / turbulence() would break nearly all of them."""
+    grad, perm = rtw.perlin_new(7)
+    scale = F(4.0)
+    rs = np.random.RandomState(21)
+    pts = rs.uniform(-6.0, 6.0, (300, 3)).astype(F)
+    with oracle.new_scene() as s:
+        tex = s.texture_noise(grad, perm, float(scale))
+        exact = 0
+        for p in pts:
+            got = oracle.texture_value(s, tex, 0.0, 0.0, p)
+            x = scale * p[2] + F(10.0) * _turbulence(grad, perm, p)
+            want = F(0.5) * (F(1.0) + F(np.sin(np.float64(x))))
+            assert got[0] == got[1] == got[2]
+            ulp = abs(int(_bits(got[:1])[0]) - int(_bits(np.array([want], F))[0]))
+            assert ulp <= 2, (p, got[0], want)
+            exact += ulp == 0
+    assert exact >= 0.98 * len(pts), exact
+
+
+def test_checker_uvdebug_and_image_textures_against_numpy(oracle):
+    """texture.rs:62-81 (sign of the product of three sines picks odd / even), :97-104 (uv as colour), image_texture.rs:34-51 (clamp, flip v,
+    truncate, clamp the index, / 255 as a multiplication by 1/255)"""
+    rs = np.random.RandomState(5)
+    img = rs.randint(0, 256, (7, 5, 3)).astype(np.uint8)      # height 7, width 5
+    with oracle.new_scene() as s:
+        odd, even = s.texture_solid(.2, .3, .1), s.texture_solid(.9, .9, .9)
+        chk = s.texture_checker(odd, even, 10.0)
+        uvd = s.texture_uvdebug()
+        imt = s.texture_image(img)
+        for _ in range(300):
+            p = rs.uniform(-3, 3, 3).astype(F)
+            u, v = (F(x) for x in rs.uniform(-0.2, 1.2, 2))
+            sines = np.sin(np.float64(F(10.0) * p[0])) * np.sin(np.float64(F(10.0) * p[1])) * np.sin(np.float64(F(10.0) * p[2]))
+            if abs(sines) > 1e-5:                                 # away from the sign change, where libm's last bit cannot matter
+                want = (.2, .3, .1) if sines < 0 else (.9, .9, .9)
+                np.testing.assert_array_equal(oracle.texture_value(s, chk, float(u), float(v), p), np.array(want, F))
+            np.testing.assert_array_equal(oracle.texture_value(s, uvd, float(u), float(v), p), _v(u, v, 0))
+            uc = np.clip(u, F(0), F(1))
+            vc = F(1.0) - np.clip(v, F(0), F(1))
+            i = min(max(int(uc * F(5)), 0), 4)
+            j = min(max(int(vc * F(7)), 0), 6)
+            want = img[j, i].astype(F) * (F(1.0) / F(255.0))
+            assert np.array_equal(_bits(oracle.texture_value(s, imt, float(u), float(v), p)), _bits(want))
