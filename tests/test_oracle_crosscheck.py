@@ -656,3 +656,53 @@ def test_checker_uvdebug_and_image_textures_against_numpy(oracle):
             j = min(max(int(vc * F(7)), 0), 6)
             want = img[j, i].astype(F) * (F(1.0) / F(255.0))
             assert np.array_equal(_bits(oracle.texture_value(s, imt, float(u), float(v), p)), _bits(want))
+
+
+def test_constant_medium_against_numpy(oracle):
+    """volumes.rs:38-78 over a sphere boundary: two boundary queries ((-inf, inf), then (t1 + 0.0001, inf)), clamp to the window, max(0),
+    hit_distance = (-1 / density) * log10(xi) — log10, the reference's quirk — and t = t1 + hit_distance / |d|; normal (1, 0, 0), front
+    face true.  xi is this repo's keyed draw (DESIGN.md §4): word 0 of Philox block (medium id, 0x80000000 | stage) under the path's key;
+    a bare ray batch has the all-zero key."""
+    import ctypes as C
+    c, r, density = _v(0.1, 0.2, -0.3), F(1.4), F(0.9)
+    ctr = (C.c_uint32 * 4)(0, 0x80000000, 0, 0)      # medium id 0, stage 0, seed 0
+    key = (C.c_uint32 * 2)(0, 0)
+    out = (C.c_uint32 * 4)()
+    oracle.fn("philox4x32_10")(ctr, key, out)
+    xi = F(out[0] >> 8) * F(1.0 / 16777216.0)
+    with oracle.new_scene() as s:
+        s.begin_medium(float(density), s.texture_solid(.2, .4, .9))
+        s.sphere(tuple(map(float, c)), float(r), s.dielectric(1.5))
+        s.end_medium()
+        s.build()
+        o, d = _rays(5000, 31)
+        h = _trace(s, o, d)
+    neg_inv = F(-1.0) / density
+    hit_distance = neg_inv * F(np.log10(np.float64(xi)))
+    n_hit = n_miss = 0
+    for i in range(len(o)):
+        rec1 = _sphere_hit(o[i], d[i], c, r, F(-np.inf), F(np.inf))
+        rec2 = _sphere_hit(o[i], d[i], c, r, rec1[0] + F(0.0001), F(np.inf)) if rec1 else None
+        want = None
+        if rec1 and rec2:
+            t1, t2 = max(rec1[0], F(0.001)), min(rec2[0], F(np.inf))
+            if not t1 >= t2:
+                t1 = max(t1, F(0.0))
+                length = np.sqrt(_dot(d[i], d[i]))
+                inside = (t2 - t1) * length
+                margin = abs(float(hit_distance) - float(inside))
+                if margin < 1e-4 * float(inside):
+                    continue                                   # at the threshold: libm's log10 may decide
+                if not hit_distance > inside:
+                    want = t1 + hit_distance / length
+        if want is None:
+            assert h["prim_id"][i] < 0, i
+            n_miss += 1
+        else:
+            assert h["prim_id"][i] == 0
+            np.testing.assert_allclose(h["t"][i], want, rtol=1e-6)
+            np.testing.assert_allclose(h["p"][i], o[i] + h["t"][i] * d[i], rtol=1e-6, atol=1e-6)
+            np.testing.assert_array_equal(h["normal"][i], _v(1, 0, 0))
+            assert h["front_face"][i] == 1
+            n_hit += 1
+    assert n_hit > 300 and n_miss > 100
