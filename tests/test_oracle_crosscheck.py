@@ -415,11 +415,13 @@ def test_tiny_path_tracer_equals_the_oracle_frame(oracle):
     ground = dict(kind="sphere", c=_v(0, -100.5, -1), r=F(100.0), mat=("lambert", _v(0.8, 0.7, 0.2)))
     ball = dict(kind="sphere", c=_v(0.3, 0.0, -1.2), r=F(0.5), mat=("metal", _v(0.8, 0.8, 0.9), F(0.3)))
     lamp = dict(kind="xz", x0=F(-1.5), x1=F(1.5), z0=F(-2.5), z1=F(0.5), k=F(1.6), mat=("light", _v(3.0, 2.5, 2.0)))
-    objects = [ground, ball, lamp]
+    glass = dict(kind="sphere", c=_v(-0.7, -0.1, -0.6), r=F(0.4), mat=("glass", F(1.5)))
+    objects = [ground, ball, lamp, glass]
     with oracle.new_scene() as s:
         s.sphere(tuple(map(float, ground["c"])), float(ground["r"]), s.lambertian_rgb(0.8, 0.7, 0.2))
         s.sphere(tuple(map(float, ball["c"])), float(ball["r"]), s.metal(0.8, 0.8, 0.9, 0.3))
         s.xz_rect(-1.5, 1.5, -2.5, 0.5, 1.6, s.diffuse_light(s.texture_solid(3.0, 2.5, 2.0)))
+        s.sphere(tuple(map(float, glass["c"])), float(glass["r"]), s.dielectric(1.5))
         s.build()
         cam = oracle.camera_new((0.2, 0.6, 2.5), (0, 0, -1), (0, 1, 0), 50.0, w / h, 0.15, 3.4)
         p = s.params(w, h, spp, seed=seed, slices=1, background=tuple(map(float, background)))
@@ -460,6 +462,24 @@ def test_tiny_path_tracer_equals_the_oracle_frame(oracle):
             if (np.abs(out) < F(1e-8)).all():
                 out = normal
             att = mat[1]
+        elif mat[0] == "glass":                      # material.rs:100-147
+            ratio = F(1.0) / mat[1] if front else mat[1]
+            ud = _unit(d)
+            cos_t = np.minimum(_dot(-ud, normal), F(1.0))
+            sin_t = np.sqrt(F(1.0) - cos_t * cos_t)
+            reflect_it = ratio * sin_t > F(1.0)
+            if not reflect_it:
+                r0_ = (F(1.0) - ratio) / (F(1.0) + ratio)
+                r0_ = r0_ * r0_
+                x = F(1.0) - cos_t
+                x2 = x * x
+                reflect_it = r0_ + (F(1.0) - r0_) * (x * (x2 * x2)) > rng.gen()
+            if reflect_it:
+                out = _reflect(ud, normal)
+            else:
+                perp = ratio * (ud + np.minimum(_dot(-ud, normal), F(1.0)) * normal)
+                out = perp + (-np.sqrt(np.abs(F(1.0) - _dot(perp, perp)))) * normal
+            att = _v(1, 1, 1)
         else:
             refl = _reflect(_unit(d), normal)
             while True:
