@@ -32,6 +32,8 @@ def _ensure_built():
         return
     if os.environ.get("RTW_CUDA_LIB"):   # an A/B build was asked for explicitly: leave it alone
         return
+    if os.path.exists("/dev/nvidiactl"):  # a GPU box: the libraries travelled with the snapshot (built and tested here), file
+        return                            # times may not have — do not spend the box's time on a rebuild of the same code
     for d in (os.path.join(g.PKG, "csrc"), os.path.join(g.PKG, "host"), os.path.join(ROOT, "oracle")):
         try:
             g._make(d)
